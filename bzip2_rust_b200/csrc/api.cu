@@ -1,0 +1,157 @@
+// api.cu -- C ABI of libbz2b200 (include/bz2b200.h): context, staging, stage seams.
+#include "common.cuh"
+#include <string.h>
+#include <new>
+
+bz2b200_ctx::~bz2b200_ctx() {
+    cudaSetDevice(device);
+    DevBuf *all[] = {&d_T, &d_len, &d_crc, &d_SA, &d_SA2, &d_RANK, &d_F, &d_KEYA, &d_KEYB, &d_VALA, &d_VALB,
+                     &d_thist, &d_tagg, &d_cnt, &d_bwt, &d_key, &d_mtfstate, &d_chunkrec, &d_R, &d_sym, &d_m,
+                     &d_freq, &d_used, &d_agg2, &d_len6, &d_rfreq, &d_sel, &d_gbits, &d_hdr, &d_bitoff, &d_out,
+                     &d_outbits, &d_hmisc, &d_in, &d_runflag, &d_misc, &d_stream, &d_dec1, &d_dec2, &d_dec3};
+    for (DevBuf *b : all) b->release();
+    h_stage.release(); h_small.release(); h_out.release();
+    for (int i = 0; i < 8; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+extern "C" {
+
+const char *bz2b200_version(void) { return "bz2b200 0.1 (sm_100a)"; }
+
+int bz2b200_create(int device, bz2b200_ctx **out) {
+    if (!out) return BZ2B200_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return BZ2B200_E_CUDA;   // no CPU fallback
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return BZ2B200_E_CUDA; }
+    if (device >= ndev) return BZ2B200_E_ARG;
+    bz2b200_ctx *ctx = new (std::nothrow) bz2b200_ctx();
+    if (!ctx) return BZ2B200_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return BZ2B200_E_CUDA;
+    }
+    for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return BZ2B200_OK;
+}
+void bz2b200_destroy(bz2b200_ctx *ctx) { delete ctx; }
+const char *bz2b200_last_error(const bz2b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t bz2b200_launch_count(const bz2b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void bz2b200_set_timing(bz2b200_ctx *ctx, int on) { if (ctx) ctx->timing = on != 0; }
+int bz2b200_get_timing(const bz2b200_ctx *ctx, float ms[8]) {
+    if (!ctx || !ms) return BZ2B200_E_ARG;
+    memcpy(ms, ctx->stage_ms, sizeof(float) * 8);
+    return BZ2B200_OK;
+}
+int bz2b200_get_bwt_stats(const bz2b200_ctx *ctx, uint64_t st[8]) {
+    if (!ctx || !st) return BZ2B200_E_ARG;
+    memcpy(st, ctx->bwt_stats, sizeof(u64) * 8);
+    return BZ2B200_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// staging: host blocks -> fixed-stride device batch
+// ------------------------------------------------------------------------------------------
+static int bitlen32(u32 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
+
+static void batch_geometry(Batch &B, int nblk, u32 max_n) {
+    B.nblk = nblk;
+    B.max_n = max_n;
+    B.stride = ((max_n + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE;
+    B.tiles = B.stride / BZ_TILE;
+    B.nbits = bitlen32(max_n ? max_n - 1 : 0);
+    if (B.nbits < 1) B.nbits = 1;
+}
+
+int bz_stage_blocks(bz2b200_ctx *ctx, int nblk, const u8 *const *blk, const u32 *len, Batch &B) {
+    u32 max_n = 0;
+    for (int i = 0; i < nblk; i++) {
+        if (!blk[i] || len[i] == 0 || len[i] > BZ2B200_MAX_BLOCK) return BZ2B200_E_ARG;
+        if (len[i] > max_n) max_n = len[i];
+    }
+    batch_geometry(B, nblk, max_n);
+    size_t bytes = (size_t)nblk * B.stride;
+    BZ_CHECK(ctx->d_T.ensure(bytes + 64));
+    BZ_CHECK(ctx->d_len.ensure((size_t)nblk * 4));
+    // stage through pinned memory in slabs so that copies overlap the host memcpy of the next slab
+    const size_t SLAB = 64u << 20;
+    BZ_CHECK(ctx->h_stage.ensure(2 * SLAB + (size_t)nblk * 4));
+    u8 *hs = ctx->h_stage.as<u8>();
+    u32 *hlen = (u32 *)(hs + 2 * SLAB);
+    memcpy(hlen, len, (size_t)nblk * 4);
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_len.p, hlen, (size_t)nblk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int slot = 0;
+    for (int i = 0; i < nblk; i++) {
+        size_t off = 0;
+        while (off < len[i]) {
+            size_t chunk = len[i] - off < SLAB ? len[i] - off : SLAB;
+            // a slot is reused only after its previous copy has been issued two slots ago -> wait on the stream
+            if (ctx->ev[6 + slot]) cudaEventSynchronize(ctx->ev[6 + slot]);
+            memcpy(hs + (size_t)slot * SLAB, blk[i] + off, chunk);
+            BZ_CHECK(cudaMemcpyAsync(ctx->d_T.as<u8>() + (size_t)i * B.stride + off, hs + (size_t)slot * SLAB, chunk,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+            BZ_CHECK(cudaEventRecord(ctx->ev[6 + slot], ctx->stream));
+            slot ^= 1;
+            off += chunk;
+        }
+    }
+    B.T = ctx->d_T.as<u8>();
+    B.len = ctx->d_len.as<u32>();
+    return BZ2B200_OK;
+}
+
+int bz_make_batch_dev(bz2b200_ctx *ctx, int nblk, u32 stride, u32 max_n, const u8 *dT, const u32 *dlen, Batch &B) {
+    (void)ctx;
+    batch_geometry(B, nblk, max_n);
+    if (stride % BZ_TILE != 0 || stride < max_n + 64) return BZ2B200_E_ARG;
+    B.stride = stride;
+    B.tiles = stride / BZ_TILE;
+    B.T = dT;
+    B.len = dlen;
+    return BZ2B200_OK;
+}
+
+// copy per-block device regions [i*stride, i*stride + bytes_i) back to caller buffers
+template <class T>
+static int fetch_blocks(bz2b200_ctx *ctx, int nblk, const T *d_src, size_t stride_elems, const u32 *count,
+                        T *const *dst) {
+    for (int i = 0; i < nblk; i++) {
+        BZ_CHECK(cudaMemcpyAsync(dst[i], d_src + (size_t)i * stride_elems, (size_t)count[i] * sizeof(T),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    BZ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return BZ2B200_OK;
+}
+
+extern "C" {
+
+int bz2b200_bwt_encode_batch(bz2b200_ctx *ctx, int nblk, const uint8_t *const *in, const uint32_t *n,
+                             uint8_t *const *bwt, uint32_t *key) {
+    if (!ctx || nblk < 0 || (nblk && (!in || !n || !bwt || !key))) return BZ2B200_E_ARG;
+    if (nblk == 0) return BZ2B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    Batch B;
+    int rc = bz_stage_blocks(ctx, nblk, in, n, B);
+    if (rc) return rc;
+    BZ_CHECK(ctx->d_bwt.ensure((size_t)nblk * B.stride));
+    BZ_CHECK(ctx->d_key.ensure((size_t)nblk * 4));
+    rc = bz_bwt_batch(ctx, B, ctx->d_bwt.as<u8>(), ctx->d_key.as<u32>());
+    if (rc) return rc;
+    BZ_CHECK(cudaMemcpyAsync(key, ctx->d_key.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return fetch_blocks<u8>(ctx, nblk, ctx->d_bwt.as<u8>(), B.stride, n, bwt);
+}
+
+int bz2b200_bwt_encode(bz2b200_ctx *ctx, const uint8_t *in, uint32_t n, uint8_t *bwt, uint32_t *key) {
+    const uint8_t *ins[1] = {in};
+    uint8_t *outs[1] = {bwt};
+    return bz2b200_bwt_encode_batch(ctx, 1, ins, &n, outs, key);
+}
+
+}  // extern "C"

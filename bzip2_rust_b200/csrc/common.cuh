@@ -1,0 +1,174 @@
+// common.cuh -- shared internals of libbz2b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/bz2b200.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define BZ_CHECK(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            ctx->fail(#call, e_, __FILE__, __LINE__);                                      \
+            return BZ2B200_E_CUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+// Grow-only device / pinned buffers.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// Geometry shared by all per-block kernels: grid = (tiles, nblk); one bzip2 block per blockIdx.y.
+constexpr int BZ_THREADS = 256;
+constexpr int BZ_IPT = 16;
+constexpr int BZ_TILE = BZ_THREADS * BZ_IPT;   // 4096 elements per CTA tile
+constexpr int BZ_GROUP = 50;                   // Huffman group size (huffman.rs:137)
+constexpr int BZ_MAXSYM = 258;
+
+// Device-side description of a batch of RLE1 blocks (all arrays indexed by block, fixed stride).
+struct Batch {
+    int nblk;
+    u32 stride;        // elements reserved per block (multiple of BZ_TILE, >= max n + 64)
+    u32 tiles;         // stride / BZ_TILE
+    u32 max_n;
+    int nbits;         // bit length of (max_n - 1), >= 1
+    const u8 *T;       // [nblk * stride] RLE1 block bytes
+    const u32 *len;    // [nblk] block lengths (device)
+};
+
+struct bz2b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    u64 launches = 0;
+    bool timing = false;
+    bool bwt_attr_done = false;
+    float stage_ms[8] = {0};
+    u64 bwt_stats[8] = {0};
+    cudaEvent_t ev[8] = {nullptr};
+
+    // ---- batch staging ----
+    DevBuf d_T, d_len, d_crc;
+    PinBuf h_stage, h_small, h_out;
+    // ---- BWT workspace ----
+    DevBuf d_SA, d_SA2, d_RANK, d_F, d_KEYA, d_KEYB, d_VALA, d_VALB, d_thist, d_tagg, d_cnt, d_bwt, d_key;
+    // ---- MTF / RLE2 workspace ----
+    DevBuf d_mtfstate, d_chunkrec, d_R, d_sym, d_m, d_freq, d_used, d_agg2;
+    // ---- Huffman workspace ----
+    DevBuf d_len6, d_rfreq, d_sel, d_gbits, d_hdr, d_bitoff, d_out, d_outbits, d_hmisc;
+    // ---- stream / rle1 / decode ----
+    DevBuf d_in, d_runflag, d_misc, d_stream, d_dec1, d_dec2, d_dec3;
+
+    void fail(const char *what, cudaError_t e, const char *file, int line) {
+        err = std::string(what) + ": " + cudaGetErrorString(e) + " at " + file + ":" + std::to_string(line);
+    }
+    ~bz2b200_ctx();
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 warp_incl_sum(u32 v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_max(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v = max(v, t);
+    }
+    return v;
+}
+// Exclusive sum over the 256 threads of a CTA. `ws` = 8+ u32 of shared scratch. All threads call.
+__device__ __forceinline__ u32 block_excl_sum(u32 v, u32 *ws, u32 &total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 inc = warp_incl_sum(v);
+    __syncthreads();
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    u32 wsum = (lane < (int)(blockDim.x >> 5)) ? ws[lane] : 0;
+    u32 winc = warp_incl_sum(wsum);
+    u32 wbase = __shfl_sync(0xffffffffu, winc, w) - __shfl_sync(0xffffffffu, wsum, w);
+    total = __shfl_sync(0xffffffffu, winc, (blockDim.x >> 5) - 1);
+    return wbase + inc - v;
+}
+// Exclusive running max over the threads of a CTA (identity = -1). `ws` = 8+ ints of scratch.
+__device__ __forceinline__ int block_excl_max(int v, int *ws, int &total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warp_incl_max(v);
+    __syncthreads();
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    int wv = (lane < (int)(blockDim.x >> 5)) ? ws[lane] : -1;
+    int winc = warp_incl_max(wv);
+    int wprev = __shfl_up_sync(0xffffffffu, winc, 1);
+    if (lane == 0) wprev = -1;
+    int wbase = __shfl_sync(0xffffffffu, wprev, w);
+    total = __shfl_sync(0xffffffffu, winc, (blockDim.x >> 5) - 1);
+    int prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prev = -1;
+    return max(wbase, prev);
+}
+#endif
+
+// stage entry points (host side, implemented in the .cu files)
+int bz_stage_blocks(bz2b200_ctx *ctx, int nblk, const u8 *const *blk, const u32 *len, Batch &B);
+int bz_make_batch_dev(bz2b200_ctx *ctx, int nblk, u32 stride, u32 max_n, const u8 *dT, const u32 *dlen, Batch &B);
+int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt /*[nblk*stride]*/, u32 *d_key /*[nblk]*/);
+int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym /*[nblk*(stride)]*/, u32 *d_m,
+                 u32 *d_freq /*[nblk*256]*/, u8 *d_used /*[nblk*256]*/);
+struct HufOut {
+    u8 *d_out;          // [nblk * out_stride] packed bits, zero padded
+    u64 *d_bits;        // [nblk]
+    size_t out_stride;  // bytes per block, multiple of 16
+    u8 *d_len6;         // [nblk*6*258] final code lengths
+    u8 *d_sel;          // [nblk*sel_stride] selectors
+    u32 sel_stride;
+    u32 *d_ntab;        // [nblk]
+};
+// emit_header: 1 = full compress_block output (block magic, crc, rand bit, key first), 0 = huf_encode only
+int bz_huf_batch(bz2b200_ctx *ctx, const Batch &B, const u16 *d_sym, const u32 *d_m, const u32 *d_freq,
+                 const u8 *d_used, int emit_header, const u32 *d_crc, const u32 *d_key, HufOut &out);

@@ -1,0 +1,130 @@
+/*
+ * bz2b200.h -- C ABI of the B200-native bzip2 compression engine (libbz2b200.so).
+ *
+ * This is the drop-in boundary for the per-block compression hot path of
+ * ohsnyt/bzip2-rust.  The reference has no FFI layer; each entry point below names the
+ * Rust function (reference file:line) whose body a thin `extern "C"` crate would replace
+ * (INTEGRATION.md shows the binding).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - return 0 on success, negative BZ2B200_E_* otherwise; nothing ever unwinds or aborts
+ *     across this boundary (the reference panics freely; a library must not).
+ *   - functions WITHOUT the _dev suffix take HOST pointers; the library stages them
+ *     through pinned memory and copies results back.  _dev functions take DEVICE
+ *     pointers on the context's GPU (used for HBM-resident measurement).
+ *   - a context owns one GPU (streams, workspaces).  Calls on one context are serialised
+ *     by an internal mutex; use one context per GPU for multi-GPU sharding.
+ *   - there is no CPU fallback: if no CUDA device is usable, bz2b200_create fails.
+ */
+#ifndef BZ2B200_H
+#define BZ2B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bz2b200_ctx bz2b200_ctx;
+
+enum {
+    BZ2B200_OK = 0,
+    BZ2B200_E_ARG = -1,      /* bad argument (null pointer, level outside 1..9, block too large) */
+    BZ2B200_E_CAP = -2,      /* caller's output buffer too small */
+    BZ2B200_E_CUDA = -3,     /* CUDA runtime error; see bz2b200_last_error */
+    BZ2B200_E_NOMEM = -4,
+    BZ2B200_E_FORMAT = -5,   /* decoder: malformed / unsupported stream */
+    BZ2B200_E_CRC = -6       /* decoder: CRC mismatch */
+};
+
+#define BZ2B200_MAX_BLOCK 900000u   /* largest RLE1 block accepted (level 9: 899 986, rle1.rs:110) */
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* device < 0 selects the current CUDA device. */
+int  bz2b200_create(int device, bz2b200_ctx **out);
+void bz2b200_destroy(bz2b200_ctx *ctx);
+const char *bz2b200_last_error(const bz2b200_ctx *ctx);
+const char *bz2b200_version(void);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+uint64_t bz2b200_launch_count(const bz2b200_ctx *ctx);
+
+/* ---- seam: compress_block (src/compression/compress_block.rs:24), batched ---------------- */
+/* Replaces `compress_block(block:&[u8], block_crc:u32) -> (Vec<u8>, u8)` for nblk blocks at
+ * once (the reference calls it once per block from rayon workers, compress.rs:129-131).
+ * blk[i]/len[i]/crc[i]: RLE1 blocks as produced by RLE1Block::next (rle1.rs:250).
+ * out[i] receives the packed block (block magic .. last Huffman code), zero padded to a byte;
+ * out_bits[i] = exact bit length, so the reference's padding value is (8 - out_bits%8)%8. */
+int bz2b200_compress_blocks(bz2b200_ctx *ctx, int nblk, const uint8_t *const *blk, const uint32_t *len,
+                            const uint32_t *crc, uint8_t *const *out, const size_t *out_cap,
+                            uint64_t *out_bits);
+
+/* ---- seam: compress (src/compression/compress.rs:40) + BitWriter (bitwriter.rs:42-132) --- */
+/* Whole stream in memory: RLE1 + block split + CRC, all blocks, header/footer/combined CRC.
+ * Byte-identical to the reference's output file for `level` (1..9). */
+int bz2b200_compress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level,
+                            uint8_t *out, size_t out_cap, size_t *out_len);
+/* Same, input already resident in device memory, output left in device memory. */
+int bz2b200_compress_stream_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
+                                uint8_t *d_out, size_t out_cap, size_t *out_len);
+/* Upper bound of the compressed size for n input bytes (for sizing `out`). */
+size_t bz2b200_compress_bound(size_t n);
+
+/* Multi-GPU sharding helpers: compress only blocks [first, first+count) of the
+ * stream's block sequence and return them as one bit string WITHOUT stream header/footer.
+ * block_crcs receives the per-block CRCs so the caller can fold the combined CRC in order.
+ * The host merges the pieces with bz2b200_merge_streams. */
+int bz2b200_stream_plan(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level,
+                        uint64_t *block_start /* cap entries */, uint32_t cap, uint32_t *nblocks);
+int bz2b200_compress_range(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level,
+                           const uint64_t *block_start, uint32_t nblocks_total,
+                           uint32_t first, uint32_t count,
+                           uint8_t *out, size_t out_cap, uint64_t *out_bits, uint32_t *block_crcs);
+/* Ordered concatenation at bit granularity + "BZh<level>" header + footer with combined CRC
+ * (bitwriter.rs:67-72, :89-114; crc.rs:25-27).  Pure host code. */
+int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, const uint64_t *part_bits,
+                          const uint32_t *const *part_crcs, const uint32_t *part_ncrc,
+                          uint8_t *out, size_t out_cap, size_t *out_len);
+
+/* ---- stage seams (used by the parity tests, one per reference function) ------------------ */
+/* do_crc (src/tools/crc.rs:15) */
+int bz2b200_crc32(bz2b200_ctx *ctx, const uint8_t *data, size_t n, uint32_t *crc);
+/* RLE1Block::next (src/tools/rle1.rs:250): all blocks of a stream at once.
+ * blocks are written back to back into rle1_out; block i spans
+ * [rle1_off[i], rle1_off[i+1]) and covers input [in_off[i], in_off[i+1]). */
+int bz2b200_rle1_split(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level,
+                       uint8_t *rle1_out, size_t rle1_cap, uint64_t *rle1_off, uint64_t *in_off,
+                       uint32_t *crc, uint32_t cap_blocks, uint32_t *nblocks);
+/* bwt_encode (src/bwt_algorithms/bwt_sort.rs:27): true cyclic-rotation BWT, key = first row of
+ * the class of rotation 0 (the reference's native path; see DESIGN.md for the SA-IS divergence) */
+int bz2b200_bwt_encode(bz2b200_ctx *ctx, const uint8_t *in, uint32_t n, uint8_t *bwt, uint32_t *key);
+int bz2b200_bwt_encode_batch(bz2b200_ctx *ctx, int nblk, const uint8_t *const *in, const uint32_t *n,
+                             uint8_t *const *bwt, uint32_t *key);
+/* rle2_mtf_encode (src/tools/rle2_mtf.rs:23): sym needs n+1 entries; symmap 17 entries */
+int bz2b200_mtf_rle2(bz2b200_ctx *ctx, const uint8_t *bwt, uint32_t n, uint16_t *sym, uint32_t *m,
+                     uint32_t freq[256], uint16_t symmap[17], int *nmap);
+/* huf_encode (src/huffman_coding/huffman.rs:79) on an empty BitPacker: bits of
+ * symbol map .. last code.  lengths (6*258 bytes) and selectors (ceil(m/50) bytes) are optional
+ * debug outputs. */
+int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m, const uint32_t freq[256],
+                    const uint16_t *symmap, int nmap, uint8_t *out, size_t out_cap, uint64_t *out_bits,
+                    uint8_t *lengths, uint8_t *selectors, int *table_count);
+/* bwt_decode (src/bwt_algorithms/bwt_sort.rs:91) */
+int bz2b200_bwt_decode(bz2b200_ctx *ctx, uint32_t key, const uint8_t *bwt, uint32_t n, uint8_t *out);
+/* decompress (src/compression/decompress.rs:38): single bzip2 stream, CRCs enforced */
+int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                              size_t *out_len);
+
+/* ---- measurement hooks ------------------------------------------------------------------- */
+/* Per-stage device time (ms, CUDA events on the context's stream) of the last compress call:
+ * [0]=rle1+crc+split [1]=bwt [2]=mtf/rle2 [3]=huffman select+lengths [4]=bit pack [5]=total.
+ * Only filled when enabled with bz2b200_set_timing(ctx, 1). */
+void bz2b200_set_timing(bz2b200_ctx *ctx, int on);
+int  bz2b200_get_timing(const bz2b200_ctx *ctx, float ms[8]);
+/* statistics of the last BWT batch: [0]=blocks [1]=sum n [2]=max doubling rounds
+ * [3]=sum over rounds of unresolved list lengths */
+int  bz2b200_get_bwt_stats(const bz2b200_ctx *ctx, uint64_t st[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

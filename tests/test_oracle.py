@@ -1,0 +1,155 @@
+"""T0: the oracle against the reference's own unit vectors, the SURVEY App. E known answers and libbz2."""
+import bz2
+
+import numpy as np
+import pytest
+
+from bzip2_rust_b200 import corpus
+from inputs import small_cases
+
+APP_E = {
+    b"a": "425a683931415926535919939b6b00000001002000200021184682ee48a70a120332736d60",
+    b"ab": "425a6839314159265359e993fdcd000000010030002000210082b177245385090e993fdcd0",
+    b"abc": "425a6839314159265359648cbb73000000010038002000219819846177245385090648cbb730",
+    b"abcd": "425a68393141592653593d4c334b00000001003c00200021860c30dc45dc914e14240f530cd2c0",
+    b"aaaaa": "425a683931415926535944a4303d00000241002000200020002100820b17724538509044a4303d",
+    b"hello world\n": "425a68393141592653594eece8360000025180001040000644908020002200f4420182c0d4b618fc5dc914e142413bb3a0d8",
+}
+LIBBZ2_EQUAL = [b"a", b"ab", b"abc", b"aaaaa"]   # "=" rows of App. E: same bytes as libbz2's own encoder
+
+
+def test_crc_check_value(ref):
+    assert ref.crc(b"123456789") == 0xFC891918          # crc.rs:15-22 semantics
+    assert ref.crc(b"6789", ref.crc(b"12345")) == 0xFC891918
+    assert ref.stream_crc(0x80000001, 0x5) == (0x00000003 ^ 0x5)
+
+
+def test_app_e_vectors(ref):
+    for data, hexs in APP_E.items():
+        out = ref.compress_stream(data, 9, ref.SPEC)
+        assert out.hex() == hexs, data
+        assert bz2.decompress(out) == data
+        assert ref.compress_stream(data, 9, ref.EXACT) == out
+    for data in LIBBZ2_EQUAL:
+        assert bz2.compress(data, 9).hex() == APP_E[data]
+
+
+# ---- the reference's own unit vectors --------------------------------------------------------
+def test_bitpacker_out16(ref):      # bitpacker.rs:119-127
+    bp = ref.Packer()
+    bp.out16(0b00100001_00100000)
+    bp.flush()
+    assert bp.output == b"! "
+
+
+def test_bitpacker_out24_and_loc(ref):   # bitpacker.rs:129-144
+    bp = ref.Packer()
+    bp.out24(0b00001000_00000000_00000000_00100001)
+    bp.flush()
+    assert bp.output == b"!"
+    assert bp.loc() == "[1.0]"
+    bp.out24(0b00011000_00000000_00000000_00000011)
+    bp.flush()
+    assert bp.output == bytes([33, 0, 0, 3])
+    assert bp.loc() == "[4.0]"
+
+
+def test_bitpacker_out24_short(ref):     # bitpacker.rs:146-157
+    bp = ref.Packer()
+    bp.out24(0b00000010_00000000_00000000_00000011)
+    bp.flush()
+    assert bp.output == bytes([0b11000000])
+    assert bp.padding == 6
+
+
+def test_bitpacker_out32(ref):           # bitpacker.rs:159-166
+    bp = ref.Packer()
+    bp.out32(0b00100001_00100000_00100001_00100000)
+    bp.flush()
+    assert bp.output == bytes([33, 32, 33, 32])
+
+
+def test_symbol_map_vector(ref):         # symbol_map.rs:46-52 (encode side, rle2_mtf.rs:293-322)
+    data = b"Making a silly test."
+    # any BWT permutation has the same symbol set
+    _, _, smap = ref.rle2_mtf_encode(data)
+    assert list(smap) == [11008, 32770, 4, 17754, 6208]
+    _, _, smap = ref.rle2_mtf_encode(bytes(range(256)))
+    assert list(smap) == [0xFFFF] * 17       # symbol_map.rs:55-59
+
+
+def test_lms_typing(ref):                # sais_fallback.rs:253-275
+    s, l = ref.lms_types(b"caabage")
+    assert s == [0, 1, 1, 0, 1, 0, 0, 1]      # L S S L S L L S(sentinel)
+    assert l == [0, 1, 0, 0, 1, 0, 0, 1]
+
+
+def test_buckets(ref):                   # sais_fallback.rs:351-369
+    sizes, heads, tails = ref.buckets([2, 0, 1, 1, 0, 6, 4], 7)
+    assert sizes == [2, 2, 1, 0, 1, 0, 1]
+    assert heads == [1, 3, 5, 6, 6, 7, 7]
+    assert tails == [2, 4, 5, 5, 6, 6, 7]
+
+
+def test_duval_shipped_behaviour(ref):   # sais_fallback.rs:835-899: 7 of 13 expectations hold for the shipped code
+    # the shipped duval returns the start of the last Lyndon factor
+    assert ref.duval(b"abaaaa") == 5
+    assert ref.duval(b"banana") == 5
+    assert ref.duval(b"abcd") == 0
+
+
+# ---- stage invariants ---------------------------------------------------------------------------
+def test_bwt_modes_agree_and_invert(ref):
+    for name, data in small_cases():
+        k1, b1, _ = ref.bwt_encode(data, ref.SPEC)
+        k2, b2, _ = ref.bwt_encode(data, ref.SPEC_FAST)
+        assert (k1, b1) == (k2, b2), name
+        assert ref.bwt_decode(k1, b1) == data, name
+
+
+def test_rle1_blocks_cover_input(ref):
+    data = corpus.mix1m(1).tobytes()
+    for level in (1, 5, 9):
+        pos = 0
+        blocks = list(ref.rle1_blocks(data, level))
+        for crc, blk, last, consumed in blocks:
+            span = data[pos:pos + consumed]
+            assert ref.crc(span) == crc
+            assert ref.rle1_decode_standard(blk) == span
+            assert len(blk) <= level * 100000 - 19 + 5
+            pos += consumed
+        assert pos == len(data) and blocks[-1][2]
+
+
+def test_streams_decode_with_libbz2(ref):
+    rng = np.random.default_rng(7)
+    for name, data in small_cases():
+        try:
+            out = ref.compress_stream(data, 9, ref.SPEC)
+        except ref.RefPanic:
+            continue                    # reference panics on this input
+        if data[-4:] == data[-1:] * 4 and (len(data) < 5 or data[-5] != data[-1]):
+            continue                    # exact-4 tail run: the reference emits an invalid stream (D.4)
+        assert bz2.decompress(out) == data, name
+        assert ref.decompress_stream(out) == data, name
+    for level in (1, 2, 9):
+        data = corpus.mix1m(3, 350_000).tobytes()
+        out = ref.compress_stream(data, level, ref.SPEC_FAST)
+        assert bz2.decompress(out) == data
+        assert out[:4] == b"BZh" + bytes([48 + level])
+
+
+def test_threads_do_not_change_output(ref):
+    data = corpus.text(450_000, 5).tobytes()
+    a = ref.compress_stream(data, 1, ref.SPEC, threads=1)
+    b = ref.compress_stream(data, 1, ref.SPEC, threads=4)
+    assert a == b
+
+
+def test_exact_mode_reports_sais_divergence(ref):
+    # low LMS density start -> SA-IS path; binaries/periodic data come out right, source-like text may not
+    data = (b"aaaa\xfb" * 2000 + corpus.random_walk(30000, 3).tobytes())
+    out, st = ref.compress_stream(data, 9, ref.EXACT, 1, True)
+    assert st["n_blocks"] == 1 and st["n_sais"] + st["n_native"] == 1
+    if st["n_sais_divergent"] == 0:
+        assert bz2.decompress(out) == data
