@@ -155,3 +155,47 @@ int bz2b200_bwt_encode(bz2b200_ctx *ctx, const uint8_t *in, uint32_t n, uint8_t 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// rle2_mtf_encode seam
+// ------------------------------------------------------------------------------------------
+static void symmap_from_used(const u32 ub[8], uint16_t symmap[17], int *nmap) {
+    // encode_sym_map_from_bool_map, rle2_mtf.rs:293-322: L1 word + the non-empty 16-bit L2 words
+    uint16_t maps[17];
+    memset(maps, 0, sizeof maps);
+    for (int idx = 0; idx < 256; idx++) {
+        if ((ub[idx >> 5] >> (idx & 31)) & 1) {
+            maps[0] |= (uint16_t)(0x8000 >> (idx >> 4));
+            maps[1 + (idx >> 4)] |= (uint16_t)(0x8000 >> (idx & 15));
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < 17; i++) if (maps[i]) symmap[k++] = maps[i];
+    *nmap = k;
+}
+
+extern "C" int bz2b200_mtf_rle2(bz2b200_ctx *ctx, const uint8_t *bwt, uint32_t n, uint16_t *sym, uint32_t *m,
+                                uint32_t freq[256], uint16_t symmap[17], int *nmap) {
+    if (!ctx || !bwt || !sym || !m || !freq || !symmap || !nmap || n == 0) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    Batch B;
+    const u8 *ins[1] = {bwt};
+    int rc = bz_stage_blocks(ctx, 1, ins, &n, B);      // the "block text" slot holds the BWT string here
+    if (rc) return rc;
+    BZ_CHECK(ctx->d_sym.ensure((size_t)B.stride * 2));
+    BZ_CHECK(ctx->d_m.ensure(4));
+    BZ_CHECK(ctx->d_freq.ensure(256 * 4));
+    BZ_CHECK(ctx->d_used.ensure(32));
+    rc = bz_mtf_batch(ctx, B, B.T, ctx->d_sym.as<u16>(), ctx->d_m.as<u32>(), ctx->d_freq.as<u32>(), ctx->d_used.as<u8>());
+    if (rc) return rc;
+    u32 ub[8];
+    BZ_CHECK(cudaMemcpyAsync(m, ctx->d_m.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CHECK(cudaMemcpyAsync(freq, ctx->d_freq.p, 256 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CHECK(cudaMemcpyAsync(ub, ctx->d_used.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CHECK(cudaStreamSynchronize(ctx->stream));
+    BZ_CHECK(cudaMemcpyAsync(sym, ctx->d_sym.p, (size_t)(*m) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CHECK(cudaStreamSynchronize(ctx->stream));
+    symmap_from_used(ub, symmap, nmap);
+    return BZ2B200_OK;
+}

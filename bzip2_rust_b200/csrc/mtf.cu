@@ -1,0 +1,319 @@
+// mtf.cu -- move-to-front + RUNA/RUNB zero-run coding of the BWT output, batched.
+//
+// Replaces rle2_mtf_encode (reference src/tools/rle2_mtf.rs:23-177): initial MTF list = used
+// bytes ascending (:26-39), MTF rank per byte (:61-62), zero runs as bijective base-2 RUNA/RUNB
+// (:68-100), symbol = rank+1 (:106), EOB = nused+1 appended (:42,:166), the quirky freq table
+// (:72,:79,:90,:104: RUNA->freq[0], RUNB->freq[1], rank p>=1 -> freq[p]).
+//
+// The MTF recurrence is made parallel by 1024-byte chunks:
+//   k_used        used-byte bitmap of the block (256 bits).
+//   k_mtf_summary one warp per chunk: last position of every byte value inside the chunk, and
+//                 the chunk's zero-run bookkeeping.  rank 0 <=> L[i] == L[i-1] (i > 0), so the
+//                 RLE2 structure is a local property of the BWT string.
+//   k_mtf_scan    one CTA per block: running max of last positions over chunks (thread = byte
+//                 value) gives, for every chunk start, each byte's last occurrence before it --
+//                 the MTF list at the chunk start is the byte values sorted by that, descending.
+//                 A short sequential pass turns the zero-run bookkeeping into per-chunk output
+//                 offsets and pending-zero counts.
+//   k_mtf_emit    one warp per chunk: sorts the 256 values into the start list, replays the chunk
+//                 with the list held as 8 bytes per lane, and writes final u16 symbols straight
+//                 at their output offsets.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CH = 1024;              // bytes per MTF chunk (one warp)
+constexpr int WPB = BZ_THREADS / 32;  // warps (= chunks) per CTA
+
+struct ChunkAgg {
+    u32 lead;        // leading positions with rank 0 (== CH' when the whole chunk is zeros)
+    u32 count_rest;  // symbols emitted for positions at/after the first non-zero rank, runs ending inside
+    u32 trail;       // trailing zeros whose run continues into the next chunk
+    u32 flags;       // bit0: all zero, bit1: an all-zero chunk's run ends at the chunk end
+};
+
+__device__ __forceinline__ bool is_nz(const u8 *L, u32 i, u32 min_used) {
+    return i == 0 ? (L[0] != min_used) : (L[i] != L[i - 1]);
+}
+
+__global__ void __launch_bounds__(BZ_THREADS) k_used(const u8 *T, const u32 *len, u32 *usedbits, u32 stride) {
+    u32 b = blockIdx.y, n = len[b];
+    u32 base = blockIdx.x * BZ_TILE;
+    if (base >= n) return;
+    __shared__ u32 bits[8];
+    if (threadIdx.x < 8) bits[threadIdx.x] = 0;
+    __syncthreads();
+    const u8 *t = T + (size_t)b * stride;
+    u32 loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int r = 0; r < BZ_IPT; r++) {
+        u32 i = base + r * BZ_THREADS + threadIdx.x;
+        if (i < n) { u32 c = t[i]; loc[c >> 5] |= 1u << (c & 31); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        u32 v = loc[k];
+        v = __reduce_or_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0 && v) atomicOr(&bits[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && bits[threadIdx.x]) atomicOr(&usedbits[b * 8 + threadIdx.x], bits[threadIdx.x]);
+}
+
+__device__ __forceinline__ u32 min_used_of(const u32 *ub) {
+    for (int k = 0; k < 8; k++) if (ub[k]) return k * 32 + __ffs(ub[k]) - 1;
+    return 0;
+}
+
+// one warp per chunk
+__global__ void __launch_bounds__(BZ_THREADS) k_mtf_summary(const u8 *Lall, const u32 *len, const u32 *usedbits,
+                                                            int *lp, ChunkAgg *agg, u32 stride, u32 nch_stride) {
+    u32 b = blockIdx.y, n = len[b];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 c = blockIdx.x * WPB + w;
+    u32 a = c * CH;
+    __shared__ int slast[WPB][256];
+    if (a >= n) return;     // whole warp exits together; no block-level barrier below
+    u32 e = min(a + CH, n);
+    const u8 *L = Lall + (size_t)b * stride;
+    u32 min_used = min_used_of(usedbits + b * 8);
+    for (int k = lane; k < 256; k += 32) slast[w][k] = -1;
+    __syncwarp();
+    int first_nz = -1;      // position of the first non-zero rank in the chunk
+    int last_nz = -1;       // running: last non-zero position seen so far (in chunk)
+    u32 nnz = 0, digits = 0;
+    for (u32 i0 = a; i0 < e; i0 += 32) {
+        u32 i = i0 + lane;
+        bool in = i < e;
+        bool nz = false, run_end = false;
+        if (in) {
+            u32 ch = L[i];
+            atomicMax(&slast[w][ch], (int)i);
+            nz = is_nz(L, i, min_used);
+            bool nz_next = (i + 1 >= n) ? true : (L[i + 1] != ch);
+            run_end = !nz && nz_next;
+        }
+        unsigned mnz = __ballot_sync(0xffffffffu, nz);
+        if (first_nz < 0 && mnz) first_nz = (int)(i0 + __ffs(mnz) - 1);
+        // last non-zero position strictly before this lane's position
+        unsigned below = mnz & ((1u << lane) - 1);
+        int prev_nz = below ? (int)(i0 + 31 - __clz(below)) : last_nz;
+        u32 d = 0;
+        if (run_end && prev_nz >= 0) {          // a run that started inside the chunk, after first_nz
+            u32 z = i - (u32)prev_nz;
+            d = 31 - __clz(z + 1);
+        }
+        d = __reduce_add_sync(0xffffffffu, d);
+        digits += d;
+        nnz += __popc(mnz);
+        if (mnz) last_nz = (int)(i0 + 31 - __clz(mnz));
+    }
+    __syncwarp();
+    int *out = lp + ((size_t)b * nch_stride + c) * 256;
+    for (int k = lane; k < 256; k += 32) out[k] = slast[w][k];
+    if (lane == 0) {
+        ChunkAgg g;
+        bool next_nz = (e >= n) ? true : (L[e] != L[e - 1]);
+        if (first_nz < 0) {
+            g.lead = e - a; g.count_rest = 0; g.trail = 0; g.flags = 1u | (next_nz ? 2u : 0u);
+        } else {
+            g.lead = (u32)first_nz - a;
+            g.count_rest = nnz + digits;
+            // trailing zeros continue into the next chunk unless the run ends at e-1
+            u32 tz = (e - 1) - (u32)last_nz;
+            g.trail = (tz > 0 && !next_nz) ? tz : 0;
+            g.flags = 0;
+        }
+        agg[(size_t)b * nch_stride + c] = g;
+    }
+}
+
+// one CTA per block
+__global__ void __launch_bounds__(256) k_mtf_scan(const u32 *len, const u32 *usedbits, const int *__restrict__ lp,
+                                                  int *__restrict__ pm, const ChunkAgg *agg, u32 *zbefore,
+                                                  u32 *ooff, u32 *m_out, u32 nch_stride) {
+    u32 b = blockIdx.x, n = len[b];
+    u32 nch = (n + CH - 1) / CH;
+    u32 s = threadIdx.x;
+    const u32 *ub = usedbits + b * 8;
+    bool used = (ub[s >> 5] >> (s & 31)) & 1;
+    u32 idx0 = 0;
+    for (u32 k = 0; k < (s >> 5); k++) idx0 += __popc(ub[k]);
+    idx0 += __popc(ub[s >> 5] & ((1u << (s & 31)) - 1));
+    int run = used ? -(int)(idx0 + 1) : -100000 - (int)s;
+    const int *src = lp + (size_t)b * nch_stride * 256;
+    int *dst = pm + (size_t)b * nch_stride * 256;
+#pragma unroll 4
+    for (u32 c = 0; c < nch; c++) {
+        int v = src[(size_t)c * 256 + s];
+        dst[(size_t)c * 256 + s] = run;
+        if (v >= 0) run = v;
+    }
+    if (threadIdx.x == 0) {
+        const ChunkAgg *g = agg + (size_t)b * nch_stride;
+        u32 zb = 0, sum = 0;
+        for (u32 c = 0; c < nch; c++) {
+            ChunkAgg x = g[c];
+            zbefore[(size_t)b * nch_stride + c] = zb;
+            ooff[(size_t)b * nch_stride + c] = sum;
+            if (x.flags & 1u) {
+                zb += x.lead;
+                if (x.flags & 2u) { sum += 31 - __clz(zb + 1); zb = 0; }
+            } else {
+                u32 z = zb + x.lead;
+                if (z) sum += 31 - __clz(z + 1);
+                sum += x.count_rest;
+                zb = x.trail;
+            }
+        }
+        m_out[b] = sum + 1;     // + EOB
+    }
+}
+
+// one warp per chunk
+__global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u32 *len, const u32 *usedbits,
+                                                         const int *pm, const u32 *zbefore, const u32 *ooff,
+                                                         const u32 *m_in, u16 *sym, u32 *freq, u32 stride,
+                                                         u32 nch_stride) {
+    u32 b = blockIdx.y, n = len[b];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 c = blockIdx.x * WPB + w;
+    u32 a = c * CH;
+    __shared__ int sval[WPB][256];
+    __shared__ __align__(8) u8 slist[WPB][256];
+    __shared__ u32 sfreq[256];
+    sfreq[threadIdx.x] = 0;
+    __syncthreads();
+    bool active = a < n;
+    u32 runa = 0, runb = 0;
+    if (active) {
+        u32 e = min(a + CH, n);
+        const u8 *L = Lall + (size_t)b * stride;
+        u16 *so = sym + (size_t)b * stride;
+        const int *v = pm + ((size_t)b * nch_stride + c) * 256;
+        for (int k = lane; k < 256; k += 32) sval[w][k] = v[k];
+        __syncwarp();
+        // start list: byte values sorted by last occurrence, most recent first
+        {
+            int mine[8]; int rk[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { mine[k] = sval[w][lane + 32 * k]; rk[k] = 0; }
+            for (int t = 0; t < 256; t++) {
+                int x = sval[w][t];
+#pragma unroll
+                for (int k = 0; k < 8; k++) rk[k] += (x > mine[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) slist[w][rk[k]] = (u8)(lane + 32 * k);
+        }
+        __syncwarp();
+        u64 lst = ((const u64 *)slist[w])[lane];   // list positions 8*lane .. 8*lane+7, position p in byte p&7
+        u32 front = slist[w][0];
+        u32 z = zbefore[(size_t)b * nch_stride + c];
+        u32 o = ooff[(size_t)b * nch_stride + c];
+        const u32 o_start = o;
+        u32 obase = o & ~31u;
+        u32 staged = 0;
+#define EMIT(SYMV)                                                                    \
+        do {                                                                          \
+            if ((o & 31u) == (u32)lane) staged = (SYMV);                              \
+            o++;                                                                      \
+            if ((o & 31u) == 0) {                                                     \
+                if (obase + lane >= o_start) so[obase + lane] = (u16)staged;          \
+                obase = o;                                                            \
+            }                                                                         \
+        } while (0)
+#define FLUSH_ZEROS()                                                                 \
+        do {                                                                          \
+            u32 zz = z + 1; int nd = 31 - __clz(zz);                                  \
+            for (int q = 0; q < nd; q++) { u32 bit = (zz >> q) & 1u; if (bit) runb++; else runa++; EMIT(bit); } \
+            z = 0;                                                                    \
+        } while (0)
+        for (u32 i0 = a; i0 < e; i0 += 32) {
+            u32 my = (i0 + lane < e) ? L[i0 + lane] : 0;
+            int cntk = (int)min(32u, e - i0);
+            for (int k = 0; k < cntk; k++) {
+                u32 ch = __shfl_sync(0xffffffffu, my, k);
+                if (ch == front) { z++; continue; }
+                if (z) FLUSH_ZEROS();
+                // locate ch in the list
+                u64 x = lst ^ (0x0101010101010101ull * ch);
+                u64 zm = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
+                unsigned bal = __ballot_sync(0xffffffffu, zm != 0);
+                int Lh = __ffs(bal) - 1;
+                int kb = (__ffsll((long long)zm) - 1) >> 3;      // byte index inside the holder lane
+                kb = __shfl_sync(0xffffffffu, kb, Lh);
+                u32 pos = (u32)Lh * 8 + (u32)kb;
+                // shift [0,pos) up by one, put ch at the front
+                u32 topbyte = (u32)(lst >> 56);
+                u32 incoming = __shfl_up_sync(0xffffffffu, topbyte, 1);
+                if (lane == 0) incoming = ch;
+                if (lane < Lh) lst = (lst << 8) | incoming;
+                else if (lane == Lh) {
+                    u64 lowmask = kb ? ((1ull << (8 * kb)) - 1) : 0ull;           // bytes below kb
+                    u64 keepmask = (kb == 7) ? 0ull : ~((1ull << (8 * (kb + 1))) - 1);   // bytes above kb
+                    lst = (lst & keepmask) | (((lst & lowmask) << 8) | incoming);
+                }
+                front = ch;
+                if (lane == 0) atomicAdd(&sfreq[pos], 1u);
+                EMIT(pos + 1);
+            }
+        }
+        bool next_nz = (e >= n) ? true : (L[e] != L[e - 1]);
+        if (z && next_nz) FLUSH_ZEROS();
+        if (e >= n) { EMIT(m_in[b] >= 1 ? 0 : 0); o--; }   // placeholder slot for EOB, rewritten below
+        // final partial flush
+        if (obase + lane >= o_start && obase + lane < o) so[obase + lane] = (u16)staged;
+        if (e >= n && lane == 0) {
+            u32 nused = 0;
+            for (int k = 0; k < 8; k++) nused += __popc(usedbits[b * 8 + k]);
+            so[m_in[b] - 1] = (u16)(nused + 1);
+        }
+#undef EMIT
+#undef FLUSH_ZEROS
+    }
+    if (lane == 0 && active) {
+        if (runa) atomicAdd(&sfreq[0], runa);
+        if (runb) atomicAdd(&sfreq[1], runb);
+    }
+    __syncthreads();
+    if (sfreq[threadIdx.x]) atomicAdd(&freq[b * 256 + threadIdx.x], sfreq[threadIdx.x]);
+}
+
+}  // namespace
+
+#define LAUNCH_OK()                                                  \
+    do {                                                             \
+        ctx->launches++;                                             \
+        cudaError_t e_ = cudaGetLastError();                         \
+        if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
+    } while (0)
+
+// d_used receives the 256-bit used bitmap per block as 8 u32 words ([nblk*8] u32 = 32 bytes/block).
+int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, u32 *d_m, u32 *d_freq,
+                 u8 *d_used) {
+    if (B.nblk == 0) return BZ2B200_OK;
+    cudaStream_t st = ctx->stream;
+    u32 nch_stride = B.stride / CH;
+    size_t nchunks = (size_t)B.nblk * nch_stride;
+    BZ_CHECK(ctx->d_mtfstate.ensure(nchunks * 256 * 4 * 2));
+    BZ_CHECK(ctx->d_chunkrec.ensure(nchunks * (sizeof(ChunkAgg) + 8)));
+    int *lp = ctx->d_mtfstate.as<int>();
+    int *pm = lp + nchunks * 256;
+    ChunkAgg *agg = ctx->d_chunkrec.as<ChunkAgg>();
+    u32 *zbefore = (u32 *)(agg + nchunks);
+    u32 *ooff = zbefore + nchunks;
+    u32 *usedbits = (u32 *)d_used;
+    BZ_CHECK(cudaMemsetAsync(usedbits, 0, (size_t)B.nblk * 32, st));
+    BZ_CHECK(cudaMemsetAsync(d_freq, 0, (size_t)B.nblk * 256 * 4, st));
+    dim3 gfull((B.max_n + BZ_TILE - 1) / BZ_TILE, B.nblk);
+    u32 maxch = (B.max_n + CH - 1) / CH;
+    dim3 gch((maxch + WPB - 1) / WPB, B.nblk);
+    k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK();
+    k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
+    k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
+    k_mtf_emit<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride,
+                                           nch_stride);
+    LAUNCH_OK();
+    return BZ2B200_OK;
+}
