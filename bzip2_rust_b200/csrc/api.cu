@@ -199,3 +199,110 @@ extern "C" int bz2b200_mtf_rle2(bz2b200_ctx *ctx, const uint8_t *bwt, uint32_t n
     symmap_from_used(ub, symmap, nmap);
     return BZ2B200_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// huf_encode seam and the batched compress_block seam
+// ------------------------------------------------------------------------------------------
+int bz_compress_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_crc, HufOut &H) {
+    size_t ne = (size_t)B.nblk * B.stride;
+    BZ_CHECK(ctx->d_bwt.ensure(ne));
+    BZ_CHECK(ctx->d_key.ensure((size_t)B.nblk * 4));
+    BZ_CHECK(ctx->d_sym.ensure(ne * 2));
+    BZ_CHECK(ctx->d_m.ensure((size_t)B.nblk * 4));
+    BZ_CHECK(ctx->d_freq.ensure((size_t)B.nblk * 256 * 4));
+    BZ_CHECK(ctx->d_used.ensure((size_t)B.nblk * 32));
+    cudaStream_t st = ctx->stream;
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
+    int rc = bz_bwt_batch(ctx, B, ctx->d_bwt.as<u8>(), ctx->d_key.as<u32>());
+    if (rc) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
+    rc = bz_mtf_batch(ctx, B, ctx->d_bwt.as<u8>(), ctx->d_sym.as<u16>(), ctx->d_m.as<u32>(), ctx->d_freq.as<u32>(),
+                      ctx->d_used.as<u8>());
+    if (rc) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
+    rc = bz_huf_batch(ctx, B, ctx->d_sym.as<u16>(), ctx->d_m.as<u32>(), ctx->d_freq.as<u32>(), ctx->d_used.as<u8>(), 1,
+                      d_crc, ctx->d_key.as<u32>(), H);
+    if (rc) return rc;
+    if (ctx->timing) {
+        cudaEventRecord(ctx->ev[3], st);
+        BZ_CHECK(cudaEventSynchronize(ctx->ev[3]));
+        cudaEventElapsedTime(&ctx->stage_ms[1], ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->stage_ms[2], ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&ctx->stage_ms[3], ctx->ev[2], ctx->ev[3]);
+    }
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_compress_blocks(bz2b200_ctx *ctx, int nblk, const uint8_t *const *blk, const uint32_t *len,
+                                       const uint32_t *crc, uint8_t *const *out, const size_t *out_cap,
+                                       uint64_t *out_bits) {
+    if (!ctx || nblk < 0 || (nblk && (!blk || !len || !crc || !out || !out_cap || !out_bits))) return BZ2B200_E_ARG;
+    if (nblk == 0) return BZ2B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    Batch B;
+    int rc = bz_stage_blocks(ctx, nblk, blk, len, B);
+    if (rc) return rc;
+    BZ_CHECK(ctx->d_crc.ensure((size_t)nblk * 4));
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_crc.p, crc, (size_t)nblk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HufOut H;
+    rc = bz_compress_batch(ctx, B, ctx->d_crc.as<u32>(), H);
+    if (rc) return rc;
+    BZ_CHECK(cudaMemcpyAsync(out_bits, H.d_bits, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nblk; i++) {
+        size_t nb = (size_t)((out_bits[i] + 7) / 8);
+        if (nb > out_cap[i]) return BZ2B200_E_CAP;
+        BZ_CHECK(cudaMemcpyAsync(out[i], H.d_out + (size_t)i * H.out_stride, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    BZ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m, const uint32_t freq[256],
+                               const uint16_t *symmap, int nmap, uint8_t *out, size_t out_cap, uint64_t *out_bits,
+                               uint8_t *lengths, uint8_t *selectors, int *table_count) {
+    if (!ctx || !sym || !freq || !symmap || !out || !out_bits || m < 2 || m > BZ2B200_MAX_BLOCK + 1 || nmap < 2 || nmap > 17)
+        return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    // used bitmap from the symbol map (decode_sym_map, symbol_map.rs:20-42)
+    u32 ub[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int k = 1;
+    for (int i = 0; i < 16; i++) {
+        if (symmap[0] & (0x8000 >> i)) {
+            if (k >= nmap) return BZ2B200_E_ARG;
+            for (int j = 0; j < 16; j++)
+                if (symmap[k] & (0x8000 >> j)) { int v = i * 16 + j; ub[v >> 5] |= 1u << (v & 31); }
+            k++;
+        }
+    }
+    Batch B;
+    B.nblk = 1; B.max_n = m; B.stride = ((m + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE; B.tiles = B.stride / BZ_TILE;
+    B.nbits = 1; B.T = nullptr; B.len = nullptr;
+    BZ_CHECK(ctx->d_sym.ensure((size_t)B.stride * 2));
+    BZ_CHECK(ctx->d_m.ensure(4));
+    BZ_CHECK(ctx->d_freq.ensure(256 * 4));
+    BZ_CHECK(ctx->d_used.ensure(32));
+    cudaStream_t st = ctx->stream;
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_sym.p, sym, (size_t)m * 2, cudaMemcpyHostToDevice, st));
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_m.p, &m, 4, cudaMemcpyHostToDevice, st));
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_freq.p, freq, 256 * 4, cudaMemcpyHostToDevice, st));
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_used.p, ub, 32, cudaMemcpyHostToDevice, st));
+    HufOut H;
+    int rc = bz_huf_batch(ctx, B, ctx->d_sym.as<u16>(), ctx->d_m.as<u32>(), ctx->d_freq.as<u32>(), ctx->d_used.as<u8>(), 0,
+                          nullptr, nullptr, H);
+    if (rc) return rc;
+    u32 misc[8];
+    BZ_CHECK(cudaMemcpyAsync(out_bits, H.d_bits, 8, cudaMemcpyDeviceToHost, st));
+    BZ_CHECK(cudaMemcpyAsync(misc, H.d_ntab, 32, cudaMemcpyDeviceToHost, st));
+    BZ_CHECK(cudaStreamSynchronize(st));
+    size_t nb = (size_t)((*out_bits + 7) / 8);
+    if (nb > out_cap) return BZ2B200_E_CAP;
+    BZ_CHECK(cudaMemcpyAsync(out, H.d_out, nb, cudaMemcpyDeviceToHost, st));
+    if (lengths) BZ_CHECK(cudaMemcpyAsync(lengths, H.d_len6, 6 * 258, cudaMemcpyDeviceToHost, st));
+    if (selectors) BZ_CHECK(cudaMemcpyAsync(selectors, H.d_sel, misc[1], cudaMemcpyDeviceToHost, st));
+    BZ_CHECK(cudaStreamSynchronize(st));
+    if (table_count) *table_count = (int)misc[0];
+    return BZ2B200_OK;
+}
