@@ -16,7 +16,8 @@ def _check(engine, ref, data, name=""):
     assert ginfo["table_count"] == rinfo["table_count"], name
     assert ginfo["selectors"] == rinfo["selectors"], "%s: selectors differ" % name
     T = rinfo["table_count"]
-    assert np.array_equal(ginfo["lengths"][:T], rinfo["lengths"][:T]), "%s: code lengths differ" % name
+    nsym = int(sym[-1]) + 1
+    assert np.array_equal(ginfo["lengths"][:T, :nsym], rinfo["lengths"][:T, :nsym]), "%s: code lengths differ" % name
     assert gbits == rbits, "%s: bit length %d vs %d" % (name, gbits, rbits)
     assert gb == rb, "%s: packed bits differ" % name
     return rinfo
@@ -42,18 +43,37 @@ def test_group_tail_sizes(engine, ref):
         _check(engine, ref, data, "seven%d" % n)
 
 
-def test_depth_limit_retry(engine, ref):
-    # Fibonacci-like frequencies force trees deeper than 17 -> weight halving (huffman_code_from_weights.rs:73-81)
+def _fib_symbols(nsym=30, seed=11):
+    """MTF/RLE2-stage output with Fibonacci symbol frequencies (drives the tree past depth 17)."""
     parts = []
     a, b = 1, 1
-    for s in range(28):
-        parts.append(bytes([s]) * a)
+    for s in range(2, nsym):
+        parts.append(np.full(a, s, dtype=np.uint16))
         a, b = b, a + b
-    rng = np.random.default_rng(11)
-    arr = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
-    rng.shuffle(arr)
-    info = _check(engine, ref, arr[:400_000].tobytes(), "fib_freq")
-    assert info["retries"] > 0
+    arr = np.concatenate(parts)
+    np.random.default_rng(seed).shuffle(arr)
+    sym = np.concatenate([arr, np.array([nsym], dtype=np.uint16)])
+    freq = np.zeros(256, dtype=np.uint32)
+    for v, c in zip(*np.unique(arr, return_counts=True)):
+        freq[v - 1] += c                      # rle2_mtf.rs:104 indexing
+    maps = [0] * 17
+    for i in range(nsym - 1):
+        maps[0] |= 0x8000 >> (i >> 4)
+        maps[1 + (i >> 4)] |= 0x8000 >> (i & 15)
+    return sym, freq, np.array([m for m in maps if m], dtype=np.uint16)
+
+
+def test_depth_limit_retry_and_tie(engine, ref):
+    # trees deeper than 17 -> weight halving (huffman_code_from_weights.rs:73-81); this input also
+    # produces one (weight, syms) tie between distinct nodes (SURVEY D.3)
+    sym, freq, smap = _fib_symbols()
+    rb, rbits, rinfo = ref.huf_encode(sym, freq, smap)
+    assert rinfo["retries"] > 0
+    gb, gbits, ginfo = engine.huf_encode(sym, freq, smap)
+    T = rinfo["table_count"]
+    assert ginfo["selectors"] == rinfo["selectors"]
+    assert np.array_equal(ginfo["lengths"][:T, :31], rinfo["lengths"][:T, :31])
+    assert (gbits, gb) == (rbits, rb)
 
 
 def test_full_size_blocks(engine, ref):
