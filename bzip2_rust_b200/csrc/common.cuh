@@ -172,3 +172,10 @@ struct HufOut {
 // emit_header: 1 = full compress_block output (block magic, crc, rand bit, key first), 0 = huf_encode only
 int bz_huf_batch(bz2b200_ctx *ctx, const Batch &B, const u16 *d_sym, const u32 *d_m, const u32 *d_freq,
                  const u8 *d_used, int emit_header, const u32 *d_crc, const u32 *d_key, HufOut &out);
+
+// rle1.cu
+int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eof, u32 off_from, u32 max_blocks,
+                   Batch &B, u32 *nblocks, u32 *consumed, std::vector<u32> *h_spans, bool plan_only);
+int bz_crc_dev(bz2b200_ctx *ctx, const u8 *d_x, u32 n, u32 *d_crc_out);
+// api.cu
+int bz_compress_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_crc, HufOut &H);

@@ -1,0 +1,527 @@
+// rle1.cu -- RLE1 run collapsing, block splitting and block CRC32 on the device.
+//
+// Replaces the RLE1Block iterator (reference src/tools/rle1.rs:33-264: refill_buffer :63,
+// get_block :89, count_dups :226, next :250) and do_crc (src/tools/crc.rs:15-22).
+//
+// The reference scans the file serially, two bytes per step, and cuts a block when
+// out_len + (cursor - start) >= block_size (rle1.rs:110).  Here the same block ends are derived
+// in closed form from three per-position arrays built by parallel scans over an
+// input window:
+//   RS[i]    start of the maximal run containing i
+//   OUT[i]   bytes the greedy RLE1 emits for [0,i) (literal 1, group start 5, rest of group 0);
+//            groups are the 255-byte chunks of a run that are >= 4 long (count_dups takes <= 251)
+//   LASTQ[i] last group start <= i
+// A single warp then walks the chain s_{k+1} = e(s_k): binary search of OUT for the first position
+// whose output offset reaches block_size-1, the cursor-parity rule of the reference's stride-2 scan
+// ("a group at q is seen at cursor q if q-start is odd, else at q+1"), and the exit cursor
+// c = start+1 | start+R | start+R+1.  A block that begins inside a run restarts the run count, so
+// its first run is parsed from the block start in closed form.
+// Finally one thread per input byte writes the RLE1 bytes straight into the fixed-stride batch
+// text array consumed by the BWT stage, and the block CRCs are computed as a polynomial in
+// X = x^(8*PIECE) over end-aligned pieces (leading zero bytes do not change a zero-init CRC).
+#include "common.cuh"
+
+namespace {
+
+constexpr u32 CRC_POLY = 0x04C11DB7u;
+constexpr int PIECE = 1024;          // bytes per CRC piece (one thread)
+constexpr u32 NOQ = 0xFFFFFFFFu;
+
+struct BlockRec {        // one per planned block, all positions window relative
+    u32 s, e;            // input span [s, e)
+    u32 re;              // end of the first run (parsed from s)
+    u32 g_last;          // end of the last group taken in this block (s if none)
+    u32 out_re;          // output bytes for [s, re)
+    u32 out_g;           // output bytes for [s, g_last)
+    u32 out_len;         // RLE1 block length
+    u32 last;            // 1 = final block of the stream
+};
+
+// ---------------------------------------------------------------------------------------
+// GF(2) helpers for CRC combination (MSB-first polynomials, bit k <-> x^k)
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline u32 gf_mul(u32 a, u32 b) {
+    u32 r = 0;
+    for (int i = 31; i >= 0; i--) {
+        r = (r << 1) ^ ((r & 0x80000000u) ? CRC_POLY : 0u);
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+__host__ __device__ inline u32 gf_pow_x8(u64 nbytes) {      // x^(8 nbytes) mod P
+    u32 result = 1, base = 0x100;                            // base = x^8
+    while (nbytes) {
+        if (nbytes & 1) result = gf_mul(result, base);
+        base = gf_mul(base, base);
+        nbytes >>= 1;
+    }
+    return result;
+}
+
+__device__ __forceinline__ void make_crc_table(u32 *tab) {
+    u32 c = threadIdx.x << 24;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ CRC_POLY : (c << 1);
+    tab[threadIdx.x] = c;
+}
+
+// ---------------------------------------------------------------------------------------
+// window scans (flat tiles over the input window; tile aggregates reuse int4 {max, max, sum})
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BZ_THREADS) k_rs_agg(const u8 *x, u32 W, int4 *tagg) {
+    u32 base = blockIdx.x * BZ_TILE;
+    u32 i0 = base + threadIdx.x * BZ_IPT;
+    int last = -1;
+#pragma unroll
+    for (int r = 0; r < BZ_IPT; r++) {
+        u32 i = i0 + r;
+        if (i < W && (i == 0 || x[i] != x[i - 1])) last = (int)i;
+    }
+    __shared__ int wsi[8];
+    int tot;
+    block_excl_max(last, wsi, tot);
+    if (threadIdx.x == 0) tagg[blockIdx.x] = make_int4(tot, -1, 0, 0);
+}
+
+// exclusive scan of tile aggregates for a flat array of `tiles` tiles (single CTA)
+__global__ void __launch_bounds__(256) k_flat_scan(int4 *tagg, u32 tiles, u32 *total_out) {
+    __shared__ int wsi[8];
+    __shared__ u32 wsu[8];
+    int ca = -1, cb = -1; u32 cc = 0;
+    for (u32 t0 = 0; t0 < tiles; t0 += 256) {
+        u32 t = t0 + threadIdx.x;
+        int4 v = (t < tiles) ? tagg[t] : make_int4(-1, -1, 0, 0);
+        int ta, tb; u32 tc;
+        int ea = block_excl_max(v.x, wsi, ta);
+        int eb = block_excl_max(v.y, wsi, tb);
+        u32 ec = block_excl_sum((u32)v.z, wsu, tc);
+        if (t < tiles) tagg[t] = make_int4(max(ea, ca), max(eb, cb), (int)(ec + cc), 0);
+        ca = max(ca, ta); cb = max(cb, tb); cc += tc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = cc;
+}
+
+__device__ __forceinline__ bool group_start_at(const u8 *x, u32 W, u32 i, u32 rs) {
+    if ((i - rs) % 255u != 0) return false;
+    if (i + 3 >= W) return false;
+    u8 c = x[i];
+    return x[i + 1] == c && x[i + 2] == c && x[i + 3] == c;
+}
+// bytes emitted "at" position i by the greedy parse (groups = 255-chunks of a run, >= 4 long)
+__device__ __forceinline__ u32 contrib_at(const u8 *x, u32 W, u32 i, u32 rs, bool &is_q) {
+    u32 cs = rs + ((i - rs) / 255u) * 255u;
+    bool grp = group_start_at(x, W, cs, rs);
+    is_q = grp && i == cs;
+    if (!grp) return 1;
+    return is_q ? 5u : 0u;
+}
+
+// writes RS and the aggregates for the second scan: y = last group start, z = emitted bytes
+__global__ void __launch_bounds__(BZ_THREADS) k_rs_apply(const u8 *x, u32 W, const int4 *tagg1, u32 *RS,
+                                                         int4 *tagg2) {
+    u32 base = blockIdx.x * BZ_TILE;
+    u32 i0 = base + threadIdx.x * BZ_IPT;
+    int last = -1;
+    bool bd[BZ_IPT];
+#pragma unroll
+    for (int r = 0; r < BZ_IPT; r++) {
+        u32 i = i0 + r;
+        bd[r] = i < W && (i == 0 || x[i] != x[i - 1]);
+        if (bd[r]) last = (int)i;
+    }
+    __shared__ int wsi[8];
+    __shared__ u32 wsu[8];
+    int tot;
+    int rs = max(block_excl_max(last, wsi, tot), tagg1[blockIdx.x].x);
+    int lq = -1; u32 sum = 0;
+#pragma unroll
+    for (int r = 0; r < BZ_IPT; r++) {
+        u32 i = i0 + r;
+        if (i < W) {
+            if (bd[r]) rs = (int)i;
+            RS[i] = (u32)rs;
+            bool isq;
+            sum += contrib_at(x, W, i, (u32)rs, isq);
+            if (isq) lq = (int)i;
+        }
+    }
+    int tq; u32 ts;
+    block_excl_max(lq, wsi, tq);
+    block_excl_sum(sum, wsu, ts);
+    if (threadIdx.x == 0) tagg2[blockIdx.x] = make_int4(-1, tq, (int)ts, 0);
+}
+
+// OUT[i] = exclusive prefix of emitted bytes (OUT[W] = total), LASTQ[i] = last group start <= i
+__global__ void __launch_bounds__(BZ_THREADS) k_out_apply(const u8 *x, u32 W, const int4 *tagg2, const u32 *RS,
+                                                          u32 *OUT, u32 *LASTQ) {
+    u32 base = blockIdx.x * BZ_TILE;
+    u32 i0 = base + threadIdx.x * BZ_IPT;
+    u32 cb[BZ_IPT]; bool qv[BZ_IPT];
+    int lq = -1; u32 sum = 0;
+#pragma unroll
+    for (int r = 0; r < BZ_IPT; r++) {
+        u32 i = i0 + r;
+        cb[r] = 0; qv[r] = false;
+        if (i < W) {
+            bool isq;
+            cb[r] = contrib_at(x, W, i, RS[i], isq);
+            qv[r] = isq;
+            sum += cb[r];
+            if (isq) lq = (int)i;
+        }
+    }
+    __shared__ int wsi[8];
+    __shared__ u32 wsu[8];
+    int tq; u32 ts;
+    int4 carry = tagg2[blockIdx.x];
+    int q = max(block_excl_max(lq, wsi, tq), carry.y);
+    u32 o = block_excl_sum(sum, wsu, ts) + (u32)carry.z;
+#pragma unroll
+    for (int r = 0; r < BZ_IPT; r++) {
+        u32 i = i0 + r;
+        if (i < W) {
+            if (qv[r]) q = (int)i;
+            OUT[i] = o;
+            LASTQ[i] = q < 0 ? NOQ : (u32)q;
+            o += cb[r];
+            if (i == W - 1) OUT[W] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the block chain (one warp; lane 0 carries the logic)
+// ---------------------------------------------------------------------------------------
+struct ChainArgs {
+    const u8 *x; const u32 *RS; const u32 *OUT; const u32 *LASTQ;
+    u32 W;            // window length
+    u32 B;            // block_size = level*100000 - 19 (compress.rs:55)
+    u32 is_eof;       // window ends at the end of the stream
+    u32 max_blocks;
+    u32 max_out;      // largest RLE1 block the batch stride can hold
+    u32 off_from;     // EOF bookkeeping: a group starting at/after this position since the last refill puts the
+                      // reference's `remaining` counter one high (rle1.rs:207) -- see DESIGN.md "EOF corner"
+    BlockRec *rec; u32 *nrec; u32 *consumed;
+};
+
+__device__ u32 run_end_from(const u32 *RS, u32 W, u32 s) {      // first p > s with RS[p] != RS[s] (or W)
+    u32 key = RS[s];
+    u32 lo = s + 1, hi = W;                                     // answer in [lo, hi]
+    while (lo < hi) {
+        u32 mid = lo + (hi - lo) / 2;
+        if (RS[mid] > key) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__device__ u32 group_end(const u8 *x, u32 W, u32 q) {           // q + 4 + dups, dups <= 251 (rle1.rs:226-241)
+    u8 c = x[q];
+    u32 p = q + 4, lim = min(W, q + 255);
+    while (p < lim && x[p] == c) p++;
+    return p;
+}
+__device__ __forceinline__ u32 exit_cursor(u32 g, long long R) {
+    if (R <= 1) return g + 1;
+    return (R & 1) ? g + (u32)R : g + (u32)R + 1;
+}
+
+__global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
+    if (threadIdx.x != 0) return;
+    const u32 W = a.W, B = a.B;
+    u32 s = 0, nb = 0;
+    const u32 margin = a.is_eof ? 0u : 1024u;
+    while (s < W && nb < a.max_blocks) {
+        BlockRec r;
+        r.s = s; r.last = 0;
+        // ---- first run, parsed from s ----
+        u32 re = run_end_from(a.RS, W, s);
+        if (!a.is_eof && re + margin > W) break;                // run may continue past the window
+        u32 Lc = re - s;
+        u32 nfull = Lc / 255u, rem = Lc % 255u;
+        u32 ng_avail = nfull + (rem >= 4 ? 1u : 0u);
+        u32 jmax = (B - 1 + 4) / 5;                             // groups j with 5j + 1 < B
+        u32 g, out_g;
+        bool done = false;
+        u32 e = 0;
+        if (ng_avail > jmax) {                                  // the size limit falls inside the first run
+            g = s + 255u * jmax; out_g = 5u * jmax;
+            e = g + 1;
+            r.re = re; r.out_re = 0;                            // unused: block ends before re
+            done = true;
+        } else {
+            g = s + 255u * nfull + (rem >= 4 ? rem : 0u);
+            out_g = 5u * ng_avail;
+            r.re = re; r.out_re = out_g + (re - g);
+        }
+        bool has_group_after_off = ng_avail > 0 && g > a.off_from;
+        if (!done) {
+            // OUTs(x) = OUT[x] + off for x >= re
+            long long off = (long long)r.out_re - (long long)a.OUT[re];
+            long long target = (long long)B - 1 - off;          // first x >= re with OUT[x] >= target
+            u32 x1;
+            if ((long long)a.OUT[W] < target) x1 = W + 1;       // never reached inside the window
+            else {
+                u32 lo = re, hi = W;
+                while (lo < hi) {
+                    u32 mid = lo + (hi - lo) / 2;
+                    if ((long long)a.OUT[mid] >= target) hi = mid; else lo = mid + 1;
+                }
+                x1 = lo;
+            }
+            u32 gl = NOQ;                                       // start of the last taken global group
+            if (x1 <= W) {
+                // the only group that can sit exactly at the limit starts in [x1, x1+3]
+                u32 hiq = min(x1 + 3, W - 1);
+                if (x1 < W) {
+                    u32 q1 = a.LASTQ[hiq];
+                    if (q1 != NOQ && q1 >= x1 && q1 >= re && (long long)a.OUT[q1] + off == (long long)B - 1) {
+                        // taken iff it is seen at cursor q1 itself: (q1 - previous group end) odd
+                        u32 gp = g;
+                        if (q1 > 0) {
+                            u32 qp = a.LASTQ[q1 - 1];
+                            if (qp != NOQ && qp >= re) gp = group_end(a.x, W, qp);
+                        }
+                        if (((q1 - gp) & 1u) == 1u) gl = q1;
+                    }
+                }
+                if (gl == NOQ && x1 > re) {
+                    u32 qp = a.LASTQ[x1 - 1];
+                    if (qp != NOQ && qp >= re) gl = qp;
+                }
+            } else if (W > re) {
+                u32 qp = a.LASTQ[W - 1];
+                if (qp != NOQ && qp >= re) gl = qp;
+            }
+            if (gl != NOQ) {
+                g = group_end(a.x, W, gl);
+                out_g = (u32)((long long)a.OUT[gl] + off + 5);
+                if (gl >= a.off_from) has_group_after_off = true;
+            } else {
+                // no global group taken: the literal stretch continues from the first run's last group
+                // (g, out_g unchanged)
+            }
+            long long R = (long long)B - (long long)out_g;
+            e = exit_cursor(g, R);
+        }
+        // ---- window / EOF handling ----
+        if (a.is_eof) {
+            u32 lim = has_group_after_off ? W - 1 : W - 2;      // size exit only at a cursor visited before the EOF arms
+            if (W < 2 || e > lim || e > W) {                     // final block takes everything (rle1.rs:115-139)
+                e = W; r.last = 1;
+                if (!done) {
+                    // every group up to the end is taken
+                    if (W > re) {
+                        u32 qp = a.LASTQ[W - 1];
+                        if (qp != NOQ && qp >= re) {
+                            long long off = (long long)r.out_re - (long long)a.OUT[re];
+                            g = group_end(a.x, W, qp);
+                            out_g = (u32)((long long)a.OUT[qp] + off + 5);
+                        }
+                    }
+                } else {
+                    // limit fell inside the first run but the file ends here: recompute as "all groups taken"
+                    g = s + 255u * nfull + (rem >= 4 ? rem : 0u);
+                    out_g = 5u * ng_avail;
+                    r.out_re = out_g + (re - g);
+                }
+            }
+        } else if (e + margin > W) {
+            break;                                              // needs bytes beyond this window
+        }
+        r.e = e; r.g_last = g; r.out_g = out_g;
+        r.out_len = out_g + (e - g);
+        if (r.out_len > a.max_out) break;                       // cannot happen for level <= 9; guards the batch stride
+        a.rec[nb++] = r;
+        s = e;
+    }
+    *a.nrec = nb;
+    *a.consumed = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// RLE1 byte emission: thread per input byte of each planned block
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BZ_THREADS) k_rle_emit(const u8 *x, u32 W, const u32 *RS, const u32 *OUT,
+                                                         const BlockRec *rec, u8 *T, u32 *len, u32 stride) {
+    u32 k = blockIdx.y;
+    BlockRec r = rec[k];
+    u32 span = r.e - r.s;
+    u32 base = blockIdx.x * BZ_TILE;
+    if (base >= span) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[k] = r.out_len;
+    u8 *out = T + (size_t)k * stride;
+    long long off = (long long)r.out_re - (long long)OUT[min(r.re, W)];
+#pragma unroll 4
+    for (int q = 0; q < BZ_IPT; q++) {
+        u32 rel = base + q * BZ_THREADS + threadIdx.x;
+        if (rel >= span) continue;
+        u32 i = r.s + rel;
+        u8 c = x[i];
+        if (i >= r.g_last) {                                    // trailing literals of the block
+            out[r.out_g + (i - r.g_last)] = c;
+        } else if (i < r.re) {                                  // first run, chunked from s
+            u32 j = (i - r.s) / 255u, cs = r.s + j * 255u;
+            u32 cl = min(255u, r.re - cs);
+            if (cl >= 4) {
+                if (i == cs) {
+                    u8 *o = out + 5u * j;
+                    o[0] = c; o[1] = c; o[2] = c; o[3] = c; o[4] = (u8)(cl - 4);
+                }
+            } else out[5u * j + (i - cs)] = c;
+        } else {                                                // global parse
+            u32 rs = RS[i];
+            u32 cs = rs + ((i - rs) / 255u) * 255u;
+            bool grp = group_start_at(x, W, cs, rs);
+            u32 o = (u32)((long long)OUT[i] + off);
+            if (!grp) out[o] = c;
+            else if (i == cs) {
+                u32 ge = group_end(x, W, cs);
+                out[o] = c; out[o + 1] = c; out[o + 2] = c; out[o + 3] = c; out[o + 4] = (u8)(ge - cs - 4);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// CRC32 (crc.rs:15-22): pieces aligned to the END of each span
+// ---------------------------------------------------------------------------------------
+// spans: [s,e) from rec (block CRCs) or a single explicit span.
+__global__ void __launch_bounds__(256) k_crc_pieces(const u8 *x, const BlockRec *rec, u32 s0, u32 e0, u32 *part,
+                                                    u32 parts_stride, u32 xp /* x^(8*PIECE) */) {
+    __shared__ u32 tab[256];
+    __shared__ u32 red[256];
+    make_crc_table(tab);
+    u32 k = blockIdx.y;
+    u32 s = rec ? rec[k].s : s0, e = rec ? rec[k].e : e0;
+    u32 span = e - s;
+    u32 npieces = (span + PIECE - 1) / PIECE;
+    u32 p = blockIdx.x * 256 + threadIdx.x;                     // piece 0 ends at e
+    __syncthreads();
+    u32 crc = 0;
+    if (p < npieces) {
+        u32 hi = e - p * PIECE;
+        u32 lo = (hi - s >= (u32)PIECE) ? hi - PIECE : s;
+        const u8 *d = x + lo;
+        u32 n = hi - lo;
+        for (u32 i = 0; i < n; i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ d[i]];
+    }
+    // CTA partial = sum_j crc_j * X^j  (j = threadIdx.x): pairwise tree with powers X^(2^l)
+    red[threadIdx.x] = crc;
+    __syncthreads();
+    u32 pw = xp;
+    for (int st = 1; st < 256; st <<= 1) {
+        u32 v = 0;
+        bool act = (threadIdx.x % (2 * st)) == 0;
+        if (act) v = red[threadIdx.x] ^ gf_mul(red[threadIdx.x + st], pw);
+        __syncthreads();
+        if (act) red[threadIdx.x] = v;
+        __syncthreads();
+        pw = gf_mul(pw, pw);
+    }
+    if (threadIdx.x == 0 && blockIdx.x * 256 < npieces) part[(size_t)k * parts_stride + blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(32) k_crc_final(const BlockRec *rec, u32 s0, u32 e0, const u32 *part,
+                                                  u32 parts_stride, u32 xp256 /* x^(8*PIECE*256) */, u32 *crc_out) {
+    u32 k = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    u32 s = rec ? rec[k].s : s0, e = rec ? rec[k].e : e0;
+    u32 span = e - s;
+    u32 npieces = (span + PIECE - 1) / PIECE;
+    u32 nparts = (npieces + 255) / 256;
+    u32 acc = 0;
+    for (int c = (int)nparts - 1; c >= 0; c--) acc = gf_mul(acc, xp256) ^ part[(size_t)k * parts_stride + c];
+    // init ~0 contributes 0xFFFFFFFF * x^(8 len); final complement (crc.rs:17,:21)
+    u32 init = gf_mul(0xFFFFFFFFu, gf_pow_x8(span));
+    crc_out[k] = ~(acc ^ init);
+}
+
+}  // namespace
+
+#define LAUNCH_OK()                                                  \
+    do {                                                             \
+        ctx->launches++;                                             \
+        cudaError_t e_ = cudaGetLastError();                         \
+        if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
+    } while (0)
+
+// Plans and emits the RLE1 blocks of one input window that is already on the device.
+// On return: *nblocks blocks were written into the context's batch text array (ctx->d_T, ctx->d_len,
+// ctx->d_crc), `B` describes them, *consumed = input bytes covered.  h_rec (optional) receives the records.
+int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eof, u32 off_from, u32 max_blocks,
+                   Batch &B, u32 *nblocks, u32 *consumed, std::vector<u32> *h_spans, bool plan_only) {
+    cudaStream_t st = ctx->stream;
+    u32 Bsz = (u32)level * 100000u - 19u;
+    u32 max_n = Bsz + 8;                                        // RLE1 block length <= B + 5
+    u32 stride = ((max_n + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE;
+    u32 tiles = (W + BZ_TILE - 1) / BZ_TILE;
+    BZ_CHECK(ctx->d_runflag.ensure(((size_t)W + 1) * 4 * 3 + 64));
+    u32 *RS = ctx->d_runflag.as<u32>();
+    u32 *OUT = RS + ((size_t)W + 1);
+    u32 *LASTQ = OUT + ((size_t)W + 1);
+    BZ_CHECK(ctx->d_misc.ensure((size_t)tiles * sizeof(int4) * 2 + (size_t)max_blocks * sizeof(BlockRec) + 256));
+    int4 *tagg1 = ctx->d_misc.as<int4>();
+    int4 *tagg2 = tagg1 + tiles;
+    BlockRec *rec = (BlockRec *)(tagg2 + tiles);
+    u32 *d_small = (u32 *)(rec + max_blocks);                   // [0]=nrec [1]=consumed
+    BZ_CHECK(ctx->h_small.ensure(64 + (size_t)max_blocks * sizeof(BlockRec)));
+
+    if (W > 0) {
+        k_rs_agg<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1); LAUNCH_OK();
+        k_flat_scan<<<1, 256, 0, st>>>(tagg1, tiles, nullptr); LAUNCH_OK();
+        k_rs_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1, RS, tagg2); LAUNCH_OK();
+        k_flat_scan<<<1, 256, 0, st>>>(tagg2, tiles, nullptr); LAUNCH_OK();
+        k_out_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg2, RS, OUT, LASTQ); LAUNCH_OK();
+    }
+    ChainArgs a;
+    a.x = d_x; a.RS = RS; a.OUT = OUT; a.LASTQ = LASTQ; a.W = W; a.B = Bsz; a.is_eof = is_eof ? 1u : 0u;
+    a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from;
+    a.rec = rec; a.nrec = d_small; a.consumed = d_small + 1;
+    k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK();
+    u32 *hs = ctx->h_small.as<u32>();
+    BZ_CHECK(cudaMemcpyAsync(hs, d_small, 8, cudaMemcpyDeviceToHost, st));
+    BZ_CHECK(cudaStreamSynchronize(st));
+    u32 nb = hs[0];
+    *nblocks = nb; *consumed = hs[1];
+    B.nblk = (int)nb; B.max_n = max_n; B.stride = stride; B.tiles = stride / BZ_TILE;
+    { int bits = 0; u32 v = max_n - 1; while (v) { bits++; v >>= 1; } B.nbits = bits; }
+    if (nb == 0) return BZ2B200_OK;
+    BZ_CHECK(ctx->d_T.ensure((size_t)nb * stride + 64));
+    BZ_CHECK(ctx->d_len.ensure((size_t)nb * 4));
+    BZ_CHECK(ctx->d_crc.ensure((size_t)nb * 4));
+    BlockRec *hrec = (BlockRec *)(hs + 16);
+    BZ_CHECK(cudaMemcpyAsync(hrec, rec, (size_t)nb * sizeof(BlockRec), cudaMemcpyDeviceToHost, st));
+    BZ_CHECK(cudaStreamSynchronize(st));
+    u32 max_span = 0;
+    for (u32 k = 0; k < nb; k++) max_span = hrec[k].e - hrec[k].s > max_span ? hrec[k].e - hrec[k].s : max_span;
+    if (h_spans) { h_spans->clear(); for (u32 k = 0; k < nb; k++) { h_spans->push_back(hrec[k].s); h_spans->push_back(hrec[k].e); h_spans->push_back(hrec[k].out_len); h_spans->push_back(hrec[k].last); } }
+    if (plan_only) return BZ2B200_OK;
+    dim3 ge((max_span + BZ_TILE - 1) / BZ_TILE, nb);
+    k_rle_emit<<<ge, BZ_THREADS, 0, st>>>(d_x, W, RS, OUT, rec, ctx->d_T.as<u8>(), ctx->d_len.as<u32>(), stride);
+    LAUNCH_OK();
+    // block CRCs
+    u32 max_pieces = (max_span + PIECE - 1) / PIECE;
+    u32 parts_stride = (max_pieces + 255) / 256;
+    BZ_CHECK(ctx->d_agg2.ensure((size_t)nb * parts_stride * 4 + 64));
+    u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
+    dim3 gc(parts_stride, nb);
+    k_crc_pieces<<<gc, 256, 0, st>>>(d_x, rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
+    k_crc_final<<<nb, 32, 0, st>>>(rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, ctx->d_crc.as<u32>()); LAUNCH_OK();
+    B.T = ctx->d_T.as<u8>();
+    B.len = ctx->d_len.as<u32>();
+    return BZ2B200_OK;
+}
+
+// CRC of one device span (do_crc seam)
+int bz_crc_dev(bz2b200_ctx *ctx, const u8 *d_x, u32 n, u32 *d_crc_out) {
+    cudaStream_t st = ctx->stream;
+    u32 pieces = (n + PIECE - 1) / PIECE;
+    u32 parts = (pieces + 255) / 256;
+    if (parts == 0) parts = 1;
+    BZ_CHECK(ctx->d_agg2.ensure((size_t)parts * 4 + 64));
+    BZ_CHECK(cudaMemsetAsync(ctx->d_agg2.p, 0, (size_t)parts * 4, st));
+    u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
+    if (n) { k_crc_pieces<<<dim3(parts, 1), 256, 0, st>>>(d_x, nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp); LAUNCH_OK(); }
+    k_crc_final<<<1, 32, 0, st>>>(nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp256, d_crc_out); LAUNCH_OK();
+    return BZ2B200_OK;
+}

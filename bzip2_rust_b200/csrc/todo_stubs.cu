@@ -5,17 +5,6 @@
 #define NOT_YET(ctx) do { if (ctx) (ctx)->err = std::string(__func__) + ": not implemented yet"; return BZ2B200_E_ARG; } while (0)
 
 extern "C" {
-int bz2b200_compress_stream(bz2b200_ctx *ctx, const uint8_t *, size_t, int, uint8_t *, size_t, size_t *) { NOT_YET(ctx); }
-int bz2b200_compress_stream_dev(bz2b200_ctx *ctx, const uint8_t *, size_t, int, uint8_t *, size_t, size_t *) { NOT_YET(ctx); }
-size_t bz2b200_compress_bound(size_t n) { return n + n / 50 + 4096; }
-int bz2b200_stream_plan(bz2b200_ctx *ctx, const uint8_t *, size_t, int, uint64_t *, uint32_t, uint32_t *) { NOT_YET(ctx); }
-int bz2b200_compress_range(bz2b200_ctx *ctx, const uint8_t *, size_t, int, const uint64_t *, uint32_t, uint32_t,
-                           uint32_t, uint8_t *, size_t, uint64_t *, uint32_t *) { NOT_YET(ctx); }
-int bz2b200_merge_streams(int, int, const uint8_t *const *, const uint64_t *, const uint32_t *const *,
-                          const uint32_t *, uint8_t *, size_t, size_t *) { return BZ2B200_E_ARG; }
-int bz2b200_crc32(bz2b200_ctx *ctx, const uint8_t *, size_t, uint32_t *) { NOT_YET(ctx); }
-int bz2b200_rle1_split(bz2b200_ctx *ctx, const uint8_t *, size_t, int, uint8_t *, size_t, uint64_t *, uint64_t *,
-                       uint32_t *, uint32_t, uint32_t *) { NOT_YET(ctx); }
 int bz2b200_bwt_decode(bz2b200_ctx *ctx, uint32_t, const uint8_t *, uint32_t, uint8_t *) { NOT_YET(ctx); }
 int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *, size_t, uint8_t *, size_t, size_t *) { NOT_YET(ctx); }
 }
