@@ -34,7 +34,8 @@ EXPORTS = [
     "bz2b200_compress_bound", "bz2b200_stream_plan", "bz2b200_compress_range", "bz2b200_merge_streams",
     "bz2b200_crc32", "bz2b200_rle1_split", "bz2b200_bwt_encode", "bz2b200_bwt_encode_batch",
     "bz2b200_mtf_rle2", "bz2b200_huffman", "bz2b200_bwt_decode", "bz2b200_decompress_stream",
-    "bz2b200_set_timing", "bz2b200_get_timing", "bz2b200_get_bwt_stats",
+    "bz2b200_set_timing", "bz2b200_get_timing", "bz2b200_get_bwt_stats", "bz2b200_kernel_stats",
+    "bz2b200_reset_kernel_stats", "bz2b200_stream_plan_dev", "bz2b200_compress_range_dev",
 ]
 
 
@@ -73,6 +74,8 @@ def load_library():
     L.bz2b200_stream_plan.argtypes = [vp, u8p, C.c_size_t, C.c_int, u64p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.bz2b200_compress_range.argtypes = [vp, u8p, C.c_size_t, C.c_int, u64p, C.c_uint32, C.c_uint32, C.c_uint32,
                                          u8p, C.c_size_t, C.POINTER(C.c_uint64), u32p]
+    L.bz2b200_stream_plan_dev.argtypes = L.bz2b200_stream_plan.argtypes
+    L.bz2b200_compress_range_dev.argtypes = L.bz2b200_compress_range.argtypes
     L.bz2b200_merge_streams.argtypes = [C.c_int, C.c_int, vp, u64p, vp, u32p, u8p, C.c_size_t, szp]
     L.bz2b200_crc32.argtypes = [vp, u8p, C.c_size_t, C.POINTER(C.c_uint32)]
     L.bz2b200_rle1_split.argtypes = [vp, u8p, C.c_size_t, C.c_int, u8p, C.c_size_t, u64p, u64p, u32p,
@@ -88,6 +91,10 @@ def load_library():
     L.bz2b200_set_timing.restype = None
     L.bz2b200_get_timing.argtypes = [vp, C.POINTER(C.c_float * 8)]
     L.bz2b200_get_bwt_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 8)]
+    L.bz2b200_kernel_stats.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64)]
+    L.bz2b200_reset_kernel_stats.argtypes = [vp]
+    L.bz2b200_reset_kernel_stats.restype = None
     _lib = L
     return L
 
@@ -246,6 +253,42 @@ class Engine:
                                                       C.byref(ln)))
         return ln.value
 
+    # ---- sharding helpers --------------------------------------------------
+    def stream_plan(self, data, level=9, dev_ptr=None):
+        """Block start offsets of the whole stream (n+1 entries, last = len).  `dev_ptr` = the data already on
+        this GPU (raw device pointer), otherwise `data` is uploaded window by window."""
+        n = data if dev_ptr is not None else _np_u8(data).size
+        cap = n // (level * 100000 - 19 - 8) + 8
+        starts = np.zeros(cap + 1, dtype=np.uint64)
+        nb = C.c_uint32()
+        if dev_ptr is not None:
+            self._chk(self._L.bz2b200_stream_plan_dev(self._h, dev_ptr, n, level, starts.ctypes.data, cap,
+                                                      C.byref(nb)))
+        else:
+            a = _np_u8(data)
+            self._chk(self._L.bz2b200_stream_plan(self._h, a.ctypes.data, a.size, level, starts.ctypes.data, cap,
+                                                  C.byref(nb)))
+        return starts[:nb.value + 1].copy()
+
+    def compress_range(self, data, level, starts, first, count, dev_ptr=None, dev_out=None, dev_out_cap=0):
+        """Blocks [first, first+count) of the stream as a bit string -> (bytes | None, nbits, crcs)."""
+        nblocks = len(starts) - 1
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        crcs = np.zeros(max(count, 1), dtype=np.uint32)
+        bits = C.c_uint64()
+        if dev_ptr is not None:
+            self._chk(self._L.bz2b200_compress_range_dev(self._h, dev_ptr, data, level, starts.ctypes.data, nblocks,
+                                                         first, count, dev_out, dev_out_cap, C.byref(bits),
+                                                         crcs.ctypes.data))
+            return None, int(bits.value), crcs[:count].copy()
+        a = _np_u8(data)
+        span = int(starts[first + count] - starts[first])
+        cap = int(self._L.bz2b200_compress_bound(span))
+        out = np.empty(cap, dtype=np.uint8)
+        self._chk(self._L.bz2b200_compress_range(self._h, a.ctypes.data, a.size, level, starts.ctypes.data, nblocks,
+                                                 first, count, out.ctypes.data, cap, C.byref(bits), crcs.ctypes.data))
+        return out[:(bits.value + 7) // 8].tobytes(), int(bits.value), crcs[:count].copy()
+
     def bwt_decode(self, key, bwt):
         a = _np_u8(bwt)
         out = np.empty(a.size, dtype=np.uint8)
@@ -266,8 +309,26 @@ class Engine:
             self._chk(rc)
             return out[:n.value].tobytes()
 
-    def set_timing(self, on=True):
-        self._L.bz2b200_set_timing(self._h, 1 if on else 0)
+    def set_timing(self, level=1):
+        """0 = off, 1 = per-stage events, 2 = also CUDA events around every kernel launch."""
+        self._L.bz2b200_set_timing(self._h, int(level))
+
+    def kernel_stats(self):
+        """-> {kernel name: (ms, launches, algorithmic bytes)} accumulated since the last reset."""
+        out = {}
+        i = 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, ln, by = C.c_double(), C.c_uint64(), C.c_uint64()
+            if self._L.bz2b200_kernel_stats(self._h, i, name, C.byref(ms), C.byref(ln), C.byref(by)) != OK:
+                break
+            if ln.value:
+                out[name.value.decode()] = (ms.value, ln.value, by.value)
+            i += 1
+        return out
+
+    def reset_kernel_stats(self):
+        self._L.bz2b200_reset_kernel_stats(self._h)
 
     def timing(self):
         ms = (C.c_float * 8)()

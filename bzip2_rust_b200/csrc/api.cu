@@ -12,6 +12,7 @@ bz2b200_ctx::~bz2b200_ctx() {
     for (DevBuf *b : all) b->release();
     h_stage.release(); h_small.release(); h_out.release();
     for (int i = 0; i < 8; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -35,13 +36,33 @@ int bz2b200_create(int device, bz2b200_ctx **out) {
         return BZ2B200_E_CUDA;
     }
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaEventCreate(&ctx->ev_total[0]);
+    cudaEventCreate(&ctx->ev_total[1]);
     *out = ctx;
     return BZ2B200_OK;
 }
 void bz2b200_destroy(bz2b200_ctx *ctx) { delete ctx; }
 const char *bz2b200_last_error(const bz2b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t bz2b200_launch_count(const bz2b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
-void bz2b200_set_timing(bz2b200_ctx *ctx, int on) { if (ctx) ctx->timing = on != 0; }
+void bz2b200_set_timing(bz2b200_ctx *ctx, int on) { if (ctx) { ctx->timing = on != 0; ctx->prof_level = on; } }
+int bz2b200_kernel_stats(bz2b200_ctx *ctx, int idx, char name[64], double *ms, uint64_t *launches, uint64_t *bytes) {
+    if (!ctx || idx < 0 || idx >= K_COUNT || !name || !ms || !launches || !bytes) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->prof_collect();
+    strncpy(name, kKernelNames[idx], 63); name[63] = 0;
+    *ms = ctx->kstat[idx].ms; *launches = ctx->kstat[idx].launches; *bytes = ctx->kstat[idx].bytes;
+    return BZ2B200_OK;
+}
+void bz2b200_reset_kernel_stats(bz2b200_ctx *ctx) {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->prof_collect();
+    for (int i = 0; i < K_COUNT; i++) ctx->kstat[i] = KStat();
+}
 int bz2b200_get_timing(const bz2b200_ctx *ctx, float ms[8]) {
     if (!ctx || !ms) return BZ2B200_E_ARG;
     memcpy(ms, ctx->stage_ms, sizeof(float) * 8);
@@ -76,6 +97,8 @@ int bz_stage_blocks(bz2b200_ctx *ctx, int nblk, const u8 *const *blk, const u32 
         if (len[i] > max_n) max_n = len[i];
     }
     batch_geometry(B, nblk, max_n);
+    B.total_n = 0;
+    for (int i = 0; i < nblk; i++) B.total_n += len[i];
     size_t bytes = (size_t)nblk * B.stride;
     BZ_CHECK(ctx->d_T.ensure(bytes + 64));
     BZ_CHECK(ctx->d_len.ensure((size_t)nblk * 4));
@@ -109,6 +132,7 @@ int bz_stage_blocks(bz2b200_ctx *ctx, int nblk, const u8 *const *blk, const u32 
 int bz_make_batch_dev(bz2b200_ctx *ctx, int nblk, u32 stride, u32 max_n, const u8 *dT, const u32 *dlen, Batch &B) {
     (void)ctx;
     batch_geometry(B, nblk, max_n);
+    B.total_n = (u64)nblk * max_n;
     if (stride % BZ_TILE != 0 || stride < max_n + 64) return BZ2B200_E_ARG;
     B.stride = stride;
     B.tiles = stride / BZ_TILE;
@@ -279,7 +303,7 @@ extern "C" int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m
     }
     Batch B;
     B.nblk = 1; B.max_n = m; B.stride = ((m + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE; B.tiles = B.stride / BZ_TILE;
-    B.nbits = 1; B.T = nullptr; B.len = nullptr;
+    B.nbits = 1; B.T = nullptr; B.len = nullptr; B.total_n = m;
     BZ_CHECK(ctx->d_sym.ensure((size_t)B.stride * 2));
     BZ_CHECK(ctx->d_m.ensure(4));
     BZ_CHECK(ctx->d_freq.ensure(256 * 4));

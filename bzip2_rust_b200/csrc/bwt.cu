@@ -456,7 +456,7 @@ size_t scatter_smem(int mode) {
 
 #define LAUNCH_OK()                                                  \
     do {                                                             \
-        ctx->launches++;                                             \
+        ctx->prof_end();                                             \
         cudaError_t e_ = cudaGetLastError();                         \
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
@@ -464,6 +464,8 @@ size_t scatter_smem(int mode) {
 int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     if (B.nblk == 0) return BZ2B200_OK;
     cudaStream_t st = ctx->stream;
+    const u64 ne_act = B.total_n;
+    u64 lsum = 0;
     size_t ne = (size_t)B.nblk * B.stride;
     BZ_CHECK(ctx->d_SA.ensure(ne * 4));
     BZ_CHECK(ctx->d_SA2.ensure(ne * 4));
@@ -498,19 +500,19 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
         RadixArgs a{};
         a.T = B.T; a.len = B.len; a.cnt = B.len; a.sa_in = src; a.sa_out = bufs[p & 1];
         a.thist = W.thist; a.stride = B.stride; a.tiles = B.tiles; a.off = 7 - p;
-        k_radix_hist<0><<<gfull, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
-        k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, B.len, B.tiles); LAUNCH_OK();
-        k_radix_scatter<0><<<gfull, BZ_THREADS, scatter_smem(0), st>>>(a); LAUNCH_OK();
+        ctx->prof_begin(K_RADIX_HIST0, ne_act * 5); k_radix_hist<0><<<gfull, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+        ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * B.tiles * 2048); k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, B.len, B.tiles); LAUNCH_OK();
+        ctx->prof_begin(K_RADIX_SCATTER0, ne_act * 9); k_radix_scatter<0><<<gfull, BZ_THREADS, scatter_smem(0), st>>>(a); LAUNCH_OK();
         src = bufs[p & 1];
     }
     cur = src;   // after 8 passes: bufs[1] = SA2
     u32 *SA = cur;
 
     // ---- 2. heads, ranks, first unresolved list ----
-    k_init_flags<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, SA, W.F, B.stride); LAUNCH_OK();
-    k_flags_agg<<<gfull, BZ_THREADS, 0, st>>>(W.F, B.len, W.tagg, B.stride, B.tiles); LAUNCH_OK();
-    k_tile_scan<<<B.nblk, 256, 0, st>>>(W.tagg, B.len, B.len, W.cnt, B.tiles, 8u); LAUNCH_OK();
-    k_init_apply<<<gfull, BZ_THREADS, 0, st>>>(W.F, B.len, SA, W.RANK, W.tagg, W.KEYA, W.VALA, B.stride, B.tiles, B.nbits);
+    ctx->prof_begin(K_INIT_FLAGS, ne_act * 13); k_init_flags<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, SA, W.F, B.stride); LAUNCH_OK();
+    ctx->prof_begin(K_FLAGS_AGG, ne_act); k_flags_agg<<<gfull, BZ_THREADS, 0, st>>>(W.F, B.len, W.tagg, B.stride, B.tiles); LAUNCH_OK();
+    ctx->prof_begin(K_TILE_SCAN, (u64)B.nblk * B.tiles * 32); k_tile_scan<<<B.nblk, 256, 0, st>>>(W.tagg, B.len, B.len, W.cnt, B.tiles, 8u); LAUNCH_OK();
+    ctx->prof_begin(K_INIT_APPLY, ne_act * 21); k_init_apply<<<gfull, BZ_THREADS, 0, st>>>(W.F, B.len, SA, W.RANK, W.tagg, W.KEYA, W.VALA, B.stride, B.tiles, B.nbits);
     LAUNCH_OK();
 
     // ---- 3. doubling rounds ----
@@ -523,32 +525,34 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
         BZ_CHECK(cudaMemcpyAsync(h_cnt, cnt_cur, (size_t)B.nblk * 4, cudaMemcpyDeviceToHost, st));
         BZ_CHECK(cudaStreamSynchronize(st));
         u32 maxc = 0;
-        for (int b = 0; b < B.nblk; b++) { if (h_cnt[b] > maxc) maxc = h_cnt[b]; listsum += h_cnt[b]; }
+        lsum = 0;
+        for (int b = 0; b < B.nblk; b++) { if (h_cnt[b] > maxc) maxc = h_cnt[b]; lsum += h_cnt[b]; }
+        listsum += lsum;
         if (maxc == 0) break;
         if (h >= (1u << 30)) { ctx->err = "bwt: doubling did not terminate"; return BZ2B200_E_CUDA; }
         rounds++;
         dim3 gl((maxc + BZ_TILE - 1) / BZ_TILE, B.nblk);
-        k_gather<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, B.len, W.RANK, K0, V0, B.stride, h, B.nbits); LAUNCH_OK();
+        ctx->prof_begin(K_GATHER, lsum * 24); k_gather<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, B.len, W.RANK, K0, V0, B.stride, h, B.nbits); LAUNCH_OK();
         for (int p = 0; p < passes; p++) {
             RadixArgs a{};
             a.T = B.T; a.len = B.len; a.cnt = cnt_cur; a.key_in = K0; a.key_out = K1; a.val_in = V0; a.val_out = V1;
             a.thist = W.thist; a.stride = B.stride; a.tiles = B.tiles; a.shift = 8 * p;
-            k_radix_hist<1><<<gl, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
-            k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, cnt_cur, B.tiles); LAUNCH_OK();
-            k_radix_scatter<1><<<gl, BZ_THREADS, scatter_smem(1), st>>>(a); LAUNCH_OK();
+            ctx->prof_begin(K_RADIX_HIST1, lsum * 8); k_radix_hist<1><<<gl, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+            ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * B.tiles * 2048); k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, cnt_cur, B.tiles); LAUNCH_OK();
+            ctx->prof_begin(K_RADIX_SCATTER1, lsum * 24); k_radix_scatter<1><<<gl, BZ_THREADS, scatter_smem(1), st>>>(a); LAUNCH_OK();
             u64 *tk = K0; K0 = K1; K1 = tk;
             u32 *tv = V0; V0 = V1; V1 = tv;
         }
         // sorted list now in (K0, V0); the next list is written to (K1, V1)
-        k_list_agg<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, K0, W.tagg, B.stride, B.tiles, B.nbits); LAUNCH_OK();
-        k_tile_scan<<<B.nblk, 256, 0, st>>>(W.tagg, cnt_cur, B.len, cnt_nxt, B.tiles, 2 * h); LAUNCH_OK();
-        k_list_apply<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, K0, V0, W.tagg, SA, W.RANK, K1, V1, B.stride, B.tiles, B.nbits);
+        ctx->prof_begin(K_LIST_AGG, lsum * 8); k_list_agg<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, K0, W.tagg, B.stride, B.tiles, B.nbits); LAUNCH_OK();
+        ctx->prof_begin(K_TILE_SCAN, (u64)B.nblk * B.tiles * 32); k_tile_scan<<<B.nblk, 256, 0, st>>>(W.tagg, cnt_cur, B.len, cnt_nxt, B.tiles, 2 * h); LAUNCH_OK();
+        ctx->prof_begin(K_LIST_APPLY, lsum * 32); k_list_apply<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, K0, V0, W.tagg, SA, W.RANK, K1, V1, B.stride, B.tiles, B.nbits);
         LAUNCH_OK();
         { u64 *tk = K0; K0 = K1; K1 = tk; u32 *tv = V0; V0 = V1; V1 = tv; }
         { u32 *tc = cnt_cur; cnt_cur = cnt_nxt; cnt_nxt = tc; }
     }
     // ---- 4. output ----
-    k_bwt_out<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, SA, W.RANK, d_bwt, d_key, B.stride); LAUNCH_OK();
-    ctx->bwt_stats[0] = (u64)B.nblk; ctx->bwt_stats[2] = rounds; ctx->bwt_stats[3] = listsum;
+    ctx->prof_begin(K_BWT_OUT, ne_act * 6); k_bwt_out<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, SA, W.RANK, d_bwt, d_key, B.stride); LAUNCH_OK();
+    ctx->bwt_stats[0] = (u64)B.nblk; ctx->bwt_stats[1] = ne_act; ctx->bwt_stats[2] = rounds; ctx->bwt_stats[3] = listsum;
     return BZ2B200_OK;
 }

@@ -70,7 +70,14 @@ struct Batch {
     int nbits;         // bit length of (max_n - 1), >= 1
     const u8 *T;       // [nblk * stride] RLE1 block bytes
     const u32 *len;    // [nblk] block lengths (device)
+    u64 total_n;       // sum of block lengths (host copy, for profiling byte counts)
 };
+
+enum KernelId { K_RADIX_HIST0, K_RADIX_SCAN, K_RADIX_SCATTER0, K_RADIX_HIST1, K_RADIX_SCATTER1, K_INIT_FLAGS, K_FLAGS_AGG, K_TILE_SCAN, K_INIT_APPLY, K_GATHER, K_LIST_AGG, K_LIST_APPLY, K_BWT_OUT, K_USED, K_MTF_SUMMARY, K_MTF_SCAN, K_MTF_EMIT, K_HUF_INIT, K_HUF_SELECT, K_HUF_LENGTHS, K_HUF_GBITS, K_HUF_LAYOUT, K_HUF_EMIT, K_RS_AGG, K_FLAT_SCAN, K_RS_APPLY, K_OUT_APPLY, K_RLE_CHAIN, K_RLE_EMIT, K_CRC_PIECES, K_CRC_FINAL, K_CONCAT, K_FOOTER, K_DEC_MISC, K_COUNT };
+static const char *const kKernelNames[] = { "k_radix_hist0", "k_radix_scan", "k_radix_scatter0", "k_radix_hist1", "k_radix_scatter1", "k_init_flags", "k_flags_agg", "k_tile_scan", "k_init_apply", "k_gather", "k_list_agg", "k_list_apply", "k_bwt_out", "k_used", "k_mtf_summary", "k_mtf_scan", "k_mtf_emit", "k_huf_init", "k_huf_select", "k_huf_lengths", "k_huf_gbits", "k_huf_layout", "k_huf_emit", "k_rs_agg", "k_flat_scan", "k_rs_apply", "k_out_apply", "k_rle_chain", "k_rle_emit", "k_crc_pieces", "k_crc_final", "k_concat", "k_footer", "k_dec_misc" };
+
+struct KStat { double ms = 0; u64 launches = 0; u64 bytes = 0; };
+struct PendingEv { int id; u64 bytes; cudaEvent_t a, b; };
 
 struct bz2b200_ctx {
     int device = 0;
@@ -83,6 +90,7 @@ struct bz2b200_ctx {
     float stage_ms[8] = {0};
     u64 bwt_stats[8] = {0};
     cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
 
     // ---- batch staging ----
     DevBuf d_T, d_len, d_crc;
@@ -95,6 +103,38 @@ struct bz2b200_ctx {
     DevBuf d_len6, d_rfreq, d_sel, d_gbits, d_hdr, d_bitoff, d_out, d_outbits, d_hmisc;
     // ---- stream / rle1 / decode ----
     DevBuf d_in, d_runflag, d_misc, d_stream, d_dec1, d_dec2, d_dec3;
+
+    // ---- per-kernel profiling (timing level 2): CUDA events around every launch ----
+    KStat kstat[K_COUNT];
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<PendingEv> pending;
+    size_t ev_used = 0;
+    int cur_id = -1;
+    int prof_level = 0;
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        return ev_pool[ev_used++];
+    }
+    void prof_begin(int id, u64 bytes) {
+        cur_id = id;
+        if (prof_level < 2) return;
+        PendingEv p; p.id = id; p.bytes = bytes; p.a = next_event(); p.b = next_event();
+        cudaEventRecord(p.a, stream);
+        pending.push_back(p);
+    }
+    void prof_end() {
+        launches++;
+        if (prof_level < 2 || pending.empty()) return;
+        cudaEventRecord(pending.back().b, stream);
+    }
+    void prof_collect() {          // call after a stream synchronize
+        for (auto &p : pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { kstat[p.id].ms += ms; kstat[p.id].launches++; kstat[p.id].bytes += p.bytes; }
+        }
+        pending.clear();
+        ev_used = 0;
+    }
 
     void fail(const char *what, cudaError_t e, const char *file, int line) {
         err = std::string(what) + ": " + cudaGetErrorString(e) + " at " + file + ":" + std::to_string(line);

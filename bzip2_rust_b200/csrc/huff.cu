@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256) k_huf_emit(const u16 *sym, const u32 *m_i
 
 #define LAUNCH_OK()                                                  \
     do {                                                             \
-        ctx->launches++;                                             \
+        ctx->prof_end();                                             \
         cudaError_t e_ = cudaGetLastError();                         \
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
@@ -446,6 +446,7 @@ int bz_huf_batch(bz2b200_ctx *ctx, const Batch &B, const u16 *d_sym, const u32 *
                  const u8 *d_used, int emit_header, const u32 *d_crc, const u32 *d_key, HufOut &out) {
     if (B.nblk == 0) return BZ2B200_OK;
     cudaStream_t st = ctx->stream;
+    const u64 ne_act = B.total_n;
     u32 maxG = (B.max_n + 1 + BZ_GROUP - 1) / BZ_GROUP;
     u32 sel_stride = ((maxG + 255) / 256) * 256;
     size_t nb = (size_t)B.nblk;
@@ -472,16 +473,16 @@ int bz_huf_batch(bz2b200_ctx *ctx, const Batch &B, const u16 *d_sym, const u32 *
     BZ_CHECK(cudaMemsetAsync(W.rfreq, 0, nb * 6 * NSYM * 4, st));
     BZ_CHECK(cudaMemsetAsync(ctx->d_out.p, 0, nb * out_stride, st));
     dim3 gg((maxG + 255) / 256, B.nblk);
-    k_huf_init<<<B.nblk, 256, 0, st>>>(d_m, d_freq, usedbits, W); LAUNCH_OK();
+    ctx->prof_begin(K_HUF_INIT, (u64)B.nblk * 4096); k_huf_init<<<B.nblk, 256, 0, st>>>(d_m, d_freq, usedbits, W); LAUNCH_OK();
     for (int iter = 0; iter < 4; iter++) {                       // huffman.rs:114
-        k_huf_select<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride); LAUNCH_OK();
-        k_huf_lengths<<<B.nblk, 192, 0, st>>>(W); LAUNCH_OK();
+        ctx->prof_begin(K_HUF_SELECT, ne_act * 2); k_huf_select<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride); LAUNCH_OK();
+        ctx->prof_begin(K_HUF_LENGTHS, (u64)B.nblk * 6 * 258 * 5); k_huf_lengths<<<B.nblk, 192, 0, st>>>(W); LAUNCH_OK();
     }
-    k_huf_gbits<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride); LAUNCH_OK();
-    k_huf_layout<<<B.nblk, 256, 0, st>>>(W, usedbits, emit_header, d_crc, d_key, ctx->d_out.as<u8>(), out_stride,
+    ctx->prof_begin(K_HUF_GBITS, ne_act * 2); k_huf_gbits<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride); LAUNCH_OK();
+    ctx->prof_begin(K_HUF_LAYOUT, (u64)B.nblk * 4096); k_huf_layout<<<B.nblk, 256, 0, st>>>(W, usedbits, emit_header, d_crc, d_key, ctx->d_out.as<u8>(), out_stride,
                                          ctx->d_outbits.as<u64>());
     LAUNCH_OK();
-    k_huf_emit<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride, ctx->d_out.as<u8>(), out_stride); LAUNCH_OK();
+    ctx->prof_begin(K_HUF_EMIT, ne_act * 3); k_huf_emit<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride, ctx->d_out.as<u8>(), out_stride); LAUNCH_OK();
     out.d_out = ctx->d_out.as<u8>();
     out.d_bits = ctx->d_outbits.as<u64>();
     out.out_stride = out_stride;

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u
 
 #define LAUNCH_OK()                                                  \
     do {                                                             \
-        ctx->launches++;                                             \
+        ctx->prof_end();                                             \
         cudaError_t e_ = cudaGetLastError();                         \
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
@@ -294,6 +294,7 @@ int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, 
                  u8 *d_used) {
     if (B.nblk == 0) return BZ2B200_OK;
     cudaStream_t st = ctx->stream;
+    const u64 ne_act = B.total_n;
     u32 nch_stride = B.stride / CH;
     size_t nchunks = (size_t)B.nblk * nch_stride;
     BZ_CHECK(ctx->d_mtfstate.ensure(nchunks * 256 * 4 * 2));
@@ -309,10 +310,10 @@ int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, 
     dim3 gfull((B.max_n + BZ_TILE - 1) / BZ_TILE, B.nblk);
     u32 maxch = (B.max_n + CH - 1) / CH;
     dim3 gch((maxch + WPB - 1) / WPB, B.nblk);
-    k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK();
-    k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
-    k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
-    k_mtf_emit<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride,
+    ctx->prof_begin(K_USED, ne_act); k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK();
+    ctx->prof_begin(K_MTF_SUMMARY, ne_act * 2); k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
+    ctx->prof_begin(K_MTF_SCAN, ne_act * 2); k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
+    ctx->prof_begin(K_MTF_EMIT, ne_act * 3); k_mtf_emit<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride,
                                            nch_stride);
     LAUNCH_OK();
     return BZ2B200_OK;

@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(32) k_crc_final(const BlockRec *rec, u32 s0, u
 
 #define LAUNCH_OK()                                                  \
     do {                                                             \
-        ctx->launches++;                                             \
+        ctx->prof_end();                                             \
         cudaError_t e_ = cudaGetLastError();                         \
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
@@ -467,17 +467,17 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     BZ_CHECK(ctx->h_small.ensure(64 + (size_t)max_blocks * sizeof(BlockRec)));
 
     if (W > 0) {
-        k_rs_agg<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1); LAUNCH_OK();
-        k_flat_scan<<<1, 256, 0, st>>>(tagg1, tiles, nullptr); LAUNCH_OK();
-        k_rs_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1, RS, tagg2); LAUNCH_OK();
-        k_flat_scan<<<1, 256, 0, st>>>(tagg2, tiles, nullptr); LAUNCH_OK();
-        k_out_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg2, RS, OUT, LASTQ); LAUNCH_OK();
+        ctx->prof_begin(K_RS_AGG, (u64)W); k_rs_agg<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1); LAUNCH_OK();
+        ctx->prof_begin(K_FLAT_SCAN, (u64)tiles * 32); k_flat_scan<<<1, 256, 0, st>>>(tagg1, tiles, nullptr); LAUNCH_OK();
+        ctx->prof_begin(K_RS_APPLY, (u64)W * 5); k_rs_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1, RS, tagg2); LAUNCH_OK();
+        ctx->prof_begin(K_FLAT_SCAN, (u64)tiles * 32); k_flat_scan<<<1, 256, 0, st>>>(tagg2, tiles, nullptr); LAUNCH_OK();
+        ctx->prof_begin(K_OUT_APPLY, (u64)W * 13); k_out_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg2, RS, OUT, LASTQ); LAUNCH_OK();
     }
     ChainArgs a;
     a.x = d_x; a.RS = RS; a.OUT = OUT; a.LASTQ = LASTQ; a.W = W; a.B = Bsz; a.is_eof = is_eof ? 1u : 0u;
     a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from;
     a.rec = rec; a.nrec = d_small; a.consumed = d_small + 1;
-    k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK();
+    ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK();
     u32 *hs = ctx->h_small.as<u32>();
     BZ_CHECK(cudaMemcpyAsync(hs, d_small, 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
@@ -493,11 +493,13 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     BZ_CHECK(cudaMemcpyAsync(hrec, rec, (size_t)nb * sizeof(BlockRec), cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
     u32 max_span = 0;
+    B.total_n = 0;
+    for (u32 k = 0; k < nb; k++) B.total_n += hrec[k].out_len;
     for (u32 k = 0; k < nb; k++) max_span = hrec[k].e - hrec[k].s > max_span ? hrec[k].e - hrec[k].s : max_span;
     if (h_spans) { h_spans->clear(); for (u32 k = 0; k < nb; k++) { h_spans->push_back(hrec[k].s); h_spans->push_back(hrec[k].e); h_spans->push_back(hrec[k].out_len); h_spans->push_back(hrec[k].last); } }
     if (plan_only) return BZ2B200_OK;
     dim3 ge((max_span + BZ_TILE - 1) / BZ_TILE, nb);
-    k_rle_emit<<<ge, BZ_THREADS, 0, st>>>(d_x, W, RS, OUT, rec, ctx->d_T.as<u8>(), ctx->d_len.as<u32>(), stride);
+    ctx->prof_begin(K_RLE_EMIT, (u64)max_span * nb * 2); k_rle_emit<<<ge, BZ_THREADS, 0, st>>>(d_x, W, RS, OUT, rec, ctx->d_T.as<u8>(), ctx->d_len.as<u32>(), stride);
     LAUNCH_OK();
     // block CRCs
     u32 max_pieces = (max_span + PIECE - 1) / PIECE;
@@ -505,8 +507,8 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     BZ_CHECK(ctx->d_agg2.ensure((size_t)nb * parts_stride * 4 + 64));
     u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
     dim3 gc(parts_stride, nb);
-    k_crc_pieces<<<gc, 256, 0, st>>>(d_x, rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
-    k_crc_final<<<nb, 32, 0, st>>>(rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, ctx->d_crc.as<u32>()); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_PIECES, 0); k_crc_pieces<<<gc, 256, 0, st>>>(d_x, rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<nb, 32, 0, st>>>(rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, ctx->d_crc.as<u32>()); LAUNCH_OK();
     B.T = ctx->d_T.as<u8>();
     B.len = ctx->d_len.as<u32>();
     return BZ2B200_OK;
@@ -522,6 +524,6 @@ int bz_crc_dev(bz2b200_ctx *ctx, const u8 *d_x, u32 n, u32 *d_crc_out) {
     BZ_CHECK(cudaMemsetAsync(ctx->d_agg2.p, 0, (size_t)parts * 4, st));
     u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
     if (n) { k_crc_pieces<<<dim3(parts, 1), 256, 0, st>>>(d_x, nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp); LAUNCH_OK(); }
-    k_crc_final<<<1, 32, 0, st>>>(nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp256, d_crc_out); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<1, 32, 0, st>>>(nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp256, d_crc_out); LAUNCH_OK();
     return BZ2B200_OK;
 }

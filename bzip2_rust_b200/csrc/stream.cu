@@ -64,7 +64,7 @@ constexpr size_t MAX_BATCH_BYTES = 272u << 20;   // RLE1 bytes per BWT batch (wo
 
 #define LAUNCH_OK()                                                  \
     do {                                                             \
-        ctx->launches++;                                             \
+        ctx->prof_end();                                             \
         cudaError_t e_ = cudaGetLastError();                         \
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
@@ -87,6 +87,7 @@ static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, 
                          u32 max_count, std::vector<u32> *crcs_out) {
     cudaStream_t st = ctx->stream;
     if (out_cap < 16) return BZ2B200_E_CAP;
+    if (ctx->timing) cudaEventRecord(ctx->ev_total[0], st);
     BZ_CHECK(cudaMemsetAsync(d_out, 0, out_cap, st));
     u64 bitpos = whole_stream ? 32 : 0;
     u32 combined = 0;
@@ -137,18 +138,20 @@ static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, 
         BZ_CHECK(ctx->d_bitoff.ensure((size_t)nb * 8));
         BZ_CHECK(cudaMemcpyAsync(ctx->d_bitoff.p, hoff.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
         dim3 gc((u32)(((maxbits + 31) / 32 + 255) / 256), nb);
-        k_concat_bits<<<gc, 256, 0, st>>>(H.d_out, H.out_stride, H.d_bits, ctx->d_bitoff.as<u64>(), (u32 *)d_out);
+        ctx->prof_begin(K_CONCAT, maxbits / 4 * nb); k_concat_bits<<<gc, 256, 0, st>>>(H.d_out, H.out_stride, H.d_bits, ctx->d_bitoff.as<u64>(), (u32 *)d_out);
         LAUNCH_OK();
         BZ_CHECK(cudaStreamSynchronize(st));                    // hoff is reused by the next batch
         pos += consumed;
         done_blocks += nb;
     }
     if (whole_stream) {
-        k_header_footer<<<1, 32, 0, st>>>((u32 *)d_out, level, bitpos, combined, 1); LAUNCH_OK();   // bitwriter.rs:103-114
+        ctx->prof_begin(K_FOOTER, 16); k_header_footer<<<1, 32, 0, st>>>((u32 *)d_out, level, bitpos, combined, 1); LAUNCH_OK();   // bitwriter.rs:103-114
         bitpos += 80;
     }
+    if (ctx->timing) cudaEventRecord(ctx->ev_total[1], st);
     BZ_CHECK(cudaStreamSynchronize(st));
     *out_bits = bitpos;
+    if (ctx->timing) cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev_total[0], ctx->ev_total[1]);
     if (ctx->timing) { ctx->stage_ms[0] = t_rle; ctx->stage_ms[1] = t_bwt; ctx->stage_ms[2] = t_mtf; ctx->stage_ms[3] = t_huf; }
     return BZ2B200_OK;
 }
@@ -360,3 +363,55 @@ int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, con
 }
 
 }  // extern "C"
+
+// ---- device-resident variants of the sharding helpers (HBM-resident measurement at N > 1) --------------
+extern "C" int bz2b200_stream_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
+                                       uint64_t *block_start, uint32_t cap, uint32_t *nblocks) {
+    if (!ctx || (!d_in && n) || !block_start || !nblocks || level < 1 || level > 9) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    size_t pos = 0;
+    u32 total = 0;
+    std::vector<u32> spans;
+    while (pos < n) {
+        size_t W = std::min(n - pos, WINDOW);
+        bool eof = pos + W == n;
+        Batch B; u32 nb = 0, consumed = 0;
+        int rc = bz_rle1_window(ctx, d_in + pos, (u32)W, level, eof, off_from_for(n, level, pos), MAX_BATCH_BLOCKS, B, &nb,
+                                &consumed, &spans, true);
+        if (rc) return rc;
+        if (nb == 0) { ctx->err = "rle1: window too small for one block"; return BZ2B200_E_ARG; }
+        if (total + nb + 1 > cap) return BZ2B200_E_CAP;
+        for (u32 k = 0; k < nb; k++) block_start[total + k] = pos + spans[4 * k];
+        total += nb;
+        pos += consumed;
+    }
+    block_start[total] = n;
+    *nblocks = total;
+    return BZ2B200_OK;
+}
+
+extern "C" int bz2b200_compress_range_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
+                                          const uint64_t *block_start, uint32_t nblocks_total, uint32_t first,
+                                          uint32_t count, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
+                                          uint32_t *block_crcs) {
+    if (!ctx || !d_in || !block_start || !d_out || !out_bits || !block_crcs || level < 1 || level > 9 ||
+        first + count > nblocks_total)
+        return BZ2B200_E_ARG;
+    *out_bits = 0;
+    if (count == 0) return BZ2B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    size_t a = (size_t)block_start[first], b = (size_t)block_start[first + count];
+    bool to_eof = (first + count == nblocks_total);
+    size_t hi = to_eof ? n : std::min(n, b + 4096);
+    std::vector<u32> crcs;
+    u64 bits = 0;
+    int rc = compress_core(ctx, d_in + a, hi - a, level, d_out, out_cap & ~(size_t)3, &bits, false, hi == n, n, a, count,
+                           &crcs);
+    if (rc) return rc;
+    if (crcs.size() != count) { ctx->err = "compress_range: block plan mismatch"; return BZ2B200_E_ARG; }
+    memcpy(block_crcs, crcs.data(), (size_t)count * 4);
+    *out_bits = bits;
+    return BZ2B200_OK;
+}

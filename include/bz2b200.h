@@ -79,6 +79,13 @@ int bz2b200_compress_range(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int le
                            const uint64_t *block_start, uint32_t nblocks_total,
                            uint32_t first, uint32_t count,
                            uint8_t *out, size_t out_cap, uint64_t *out_bits, uint32_t *block_crcs);
+/* Device-resident variants: d_in = the WHOLE stream on this context's GPU, output stays on the device. */
+int bz2b200_stream_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
+                            uint64_t *block_start, uint32_t cap, uint32_t *nblocks);
+int bz2b200_compress_range_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
+                               const uint64_t *block_start, uint32_t nblocks_total,
+                               uint32_t first, uint32_t count,
+                               uint8_t *d_out, size_t out_cap, uint64_t *out_bits, uint32_t *block_crcs);
 /* Ordered concatenation at bit granularity + "BZh<level>" header + footer with combined CRC
  * (bitwriter.rs:67-72, :89-114; crc.rs:25-27).  Pure host code. */
 int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, const uint64_t *part_bits,
@@ -117,9 +124,15 @@ int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, uin
 /* ---- measurement hooks ------------------------------------------------------------------- */
 /* Per-stage device time (ms, CUDA events on the context's stream) of the last compress call:
  * [0]=rle1+crc+split [1]=bwt [2]=mtf/rle2 [3]=huffman select+lengths [4]=bit pack [5]=total.
- * Only filled when enabled with bz2b200_set_timing(ctx, 1). */
+ * Only filled when enabled with bz2b200_set_timing(ctx, 1) (2 = also per-kernel events). */
 void bz2b200_set_timing(bz2b200_ctx *ctx, int on);
 int  bz2b200_get_timing(const bz2b200_ctx *ctx, float ms[8]);
+/* Per-kernel device time, enabled with bz2b200_set_timing(ctx, 2): CUDA events on the context's stream
+ * around every launch.  idx = 0..; returns BZ2B200_E_ARG past the last kernel.  `bytes` is the
+ * ALGORITHMIC byte count of those launches (per-element figures in DESIGN.md), not DRAM traffic. */
+int  bz2b200_kernel_stats(bz2b200_ctx *ctx, int idx, char name[64], double *ms, uint64_t *launches,
+                          uint64_t *bytes);
+void bz2b200_reset_kernel_stats(bz2b200_ctx *ctx);
 /* statistics of the last BWT batch: [0]=blocks [1]=sum n [2]=max doubling rounds
  * [3]=sum over rounds of unresolved list lengths */
 int  bz2b200_get_bwt_stats(const bz2b200_ctx *ctx, uint64_t st[8]);
