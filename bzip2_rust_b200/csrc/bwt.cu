@@ -16,6 +16,7 @@
 //   4. key = rank[0] (first row of the class of rotation 0), bwt[j] = T[(SA[j]-1) mod n].
 // One bzip2 block per blockIdx.y, tiles of 4096 elements along blockIdx.x.
 #include "common.cuh"
+#include "radix.cuh"
 
 namespace {
 
@@ -32,7 +33,9 @@ struct BwtWs {
 // --------------------------------------------------------------------------------------
 // radix sort passes (hist -> scan -> scatter).  MODE 0: initial sort, element = rotation index,
 // digit gathered from the text.  MODE 1: list sort, element = (key64, val32), digit from key.
+// Now in radix.cuh (2048-element tiles, 4 CTAs/SM); the first version below is kept for reference only.
 // --------------------------------------------------------------------------------------
+#if 0
 struct RadixArgs {
     const u8 *T; const u32 *len;   // text and block lengths
     const u32 *cnt;                // element count per block (MODE 0: len, MODE 1: list count)
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(BZ_THREADS) k_radix_scatter(RadixArgs a) {
         else { a.key_out[ob + dst] = skey[p]; a.val_out[ob + dst] = sval[p]; }
     }
 }
+#endif
 
 // --------------------------------------------------------------------------------------
 // step 2: head flags after the 8-byte sort
@@ -446,13 +450,10 @@ __global__ void __launch_bounds__(BZ_THREADS) k_bwt_out(const u8 *T, const u32 *
     }
 }
 
-size_t scatter_smem(int mode) {
-    size_t s = (8 * 256 + 256 + 256 + 8) * 4 + BZ_TILE + BZ_TILE * 4;
-    if (mode == 1) s += (size_t)BZ_TILE * 8;
-    return s + 16;
-}
-
 }  // namespace
+
+using radix::RadixArgs;
+using radix::R_TILE;
 
 #define LAUNCH_OK()                                                  \
     do {                                                             \
@@ -475,7 +476,7 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     BZ_CHECK(ctx->d_KEYB.ensure(ne * 8));
     BZ_CHECK(ctx->d_VALA.ensure(ne * 4));
     BZ_CHECK(ctx->d_VALB.ensure(ne * 4));
-    BZ_CHECK(ctx->d_thist.ensure((size_t)B.nblk * B.tiles * 256 * 4));
+    BZ_CHECK(ctx->d_thist.ensure((size_t)B.nblk * (B.stride / radix::R_TILE) * 256 * 4));
     BZ_CHECK(ctx->d_tagg.ensure((size_t)B.nblk * B.tiles * sizeof(int4)));
     BZ_CHECK(ctx->d_cnt.ensure((size_t)B.nblk * 2 * 4));
     BZ_CHECK(ctx->h_small.ensure((size_t)B.nblk * 4 + 64));
@@ -486,12 +487,9 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     W.VALA = ctx->d_VALA.as<u32>(); W.VALB = ctx->d_VALB.as<u32>();
     W.thist = ctx->d_thist.as<u32>(); W.tagg = ctx->d_tagg.as<int4>(); W.cnt = ctx->d_cnt.as<u32>();
 
-    if (!ctx->bwt_attr_done) {
-        BZ_CHECK(cudaFuncSetAttribute(k_radix_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(0)));
-        BZ_CHECK(cudaFuncSetAttribute(k_radix_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(1)));
-        ctx->bwt_attr_done = true;
-    }
     dim3 gfull((B.max_n + BZ_TILE - 1) / BZ_TILE, B.nblk);
+    dim3 gfull_r((B.max_n + R_TILE - 1) / R_TILE, B.nblk);
+    const u32 rtiles = B.stride / R_TILE;
 
     // ---- 1. initial 8-byte LSD sort (implicit keys) ----
     u32 *cur = nullptr, *src = nullptr;
@@ -499,10 +497,10 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     for (int p = 0; p < 8; p++) {
         RadixArgs a{};
         a.T = B.T; a.len = B.len; a.cnt = B.len; a.sa_in = src; a.sa_out = bufs[p & 1];
-        a.thist = W.thist; a.stride = B.stride; a.tiles = B.tiles; a.off = 7 - p;
-        ctx->prof_begin(K_RADIX_HIST0, ne_act * 5); k_radix_hist<0><<<gfull, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
-        ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * B.tiles * 2048); k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, B.len, B.tiles); LAUNCH_OK();
-        ctx->prof_begin(K_RADIX_SCATTER0, ne_act * 9); k_radix_scatter<0><<<gfull, BZ_THREADS, scatter_smem(0), st>>>(a); LAUNCH_OK();
+        a.thist = W.thist; a.stride = B.stride; a.rtiles = rtiles; a.off = 7 - p;
+        ctx->prof_begin(K_RADIX_HIST0, ne_act * 5); radix::k_radix_hist<0><<<gfull_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+        ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * rtiles * 2048); radix::k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, B.len, rtiles); LAUNCH_OK();
+        ctx->prof_begin(K_RADIX_SCATTER0, ne_act * 9); radix::k_radix_scatter<0><<<gfull_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
         src = bufs[p & 1];
     }
     cur = src;   // after 8 passes: bufs[1] = SA2
@@ -532,14 +530,15 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
         if (h >= (1u << 30)) { ctx->err = "bwt: doubling did not terminate"; return BZ2B200_E_CUDA; }
         rounds++;
         dim3 gl((maxc + BZ_TILE - 1) / BZ_TILE, B.nblk);
+        dim3 gl_r((maxc + R_TILE - 1) / R_TILE, B.nblk);
         ctx->prof_begin(K_GATHER, lsum * 24); k_gather<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, B.len, W.RANK, K0, V0, B.stride, h, B.nbits); LAUNCH_OK();
         for (int p = 0; p < passes; p++) {
             RadixArgs a{};
             a.T = B.T; a.len = B.len; a.cnt = cnt_cur; a.key_in = K0; a.key_out = K1; a.val_in = V0; a.val_out = V1;
-            a.thist = W.thist; a.stride = B.stride; a.tiles = B.tiles; a.shift = 8 * p;
-            ctx->prof_begin(K_RADIX_HIST1, lsum * 8); k_radix_hist<1><<<gl, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
-            ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * B.tiles * 2048); k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, cnt_cur, B.tiles); LAUNCH_OK();
-            ctx->prof_begin(K_RADIX_SCATTER1, lsum * 24); k_radix_scatter<1><<<gl, BZ_THREADS, scatter_smem(1), st>>>(a); LAUNCH_OK();
+            a.thist = W.thist; a.stride = B.stride; a.rtiles = rtiles; a.shift = 8 * p;
+            ctx->prof_begin(K_RADIX_HIST1, lsum * 8); radix::k_radix_hist<1><<<gl_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+            ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * rtiles * 2048); radix::k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, cnt_cur, rtiles); LAUNCH_OK();
+            ctx->prof_begin(K_RADIX_SCATTER1, lsum * 24); radix::k_radix_scatter<1><<<gl_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
             u64 *tk = K0; K0 = K1; K1 = tk;
             u32 *tv = V0; V0 = V1; V1 = tv;
         }

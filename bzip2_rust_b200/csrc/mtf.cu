@@ -182,8 +182,20 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u
     __shared__ int sval[WPB][256];
     __shared__ __align__(8) u8 slist[WPB][256];
     __shared__ u32 sfreq[256];
+    __shared__ u8 sused[256];
+    __shared__ int s_nused;
     sfreq[threadIdx.x] = 0;
+    {   // compact list of the block's used byte values (ascending)
+        const u32 *ub = usedbits + b * 8;
+        u32 t = threadIdx.x;
+        u32 before = 0;
+        for (u32 k = 0; k < (t >> 5); k++) before += __popc(ub[k]);
+        before += __popc(ub[t >> 5] & ((1u << (t & 31)) - 1));
+        if ((ub[t >> 5] >> (t & 31)) & 1) sused[before] = (u8)t;
+        if (t == 255) s_nused = (int)(before + ((ub[7] >> 31) & 1));
+    }
     __syncthreads();
+    const int nused = s_nused;
     bool active = a < n;
     u32 runa = 0, runb = 0;
     if (active) {
@@ -193,18 +205,13 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u
         const int *v = pm + ((size_t)b * nch_stride + c) * 256;
         for (int k = lane; k < 256; k += 32) sval[w][k] = v[k];
         __syncwarp();
-        // start list: byte values sorted by last occurrence, most recent first
-        {
-            int mine[8]; int rk[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) { mine[k] = sval[w][lane + 32 * k]; rk[k] = 0; }
-            for (int t = 0; t < 256; t++) {
-                int x = sval[w][t];
-#pragma unroll
-                for (int k = 0; k < 8; k++) rk[k] += (x > mine[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) slist[w][rk[k]] = (u8)(lane + 32 * k);
+        // start list: USED byte values sorted by last occurrence, most recent first (unused values never
+        // appear in the block, so list positions >= nused are never touched)
+        for (int j = lane; j < nused; j += 32) {
+            int s = sused[j];
+            int mine = sval[w][s], rk = 0;
+            for (int t = 0; t < nused; t++) rk += (sval[w][sused[t]] > mine);
+            slist[w][rk] = (u8)s;
         }
         __syncwarp();
         u64 lst = ((const u64 *)slist[w])[lane];   // list positions 8*lane .. 8*lane+7, position p in byte p&7

@@ -205,9 +205,35 @@ struct ChainArgs {
     BlockRec *rec; u32 *nrec; u32 *consumed;
 };
 
+// Warp-cooperative lower bound on the monotone array OUT: first x in [lo, hi] with OUT[x] >= target
+// (the caller guarantees OUT[hi] >= target).  32 probes per step instead of one: ~6 dependent loads for 1e8.
+__device__ u32 warp_lower_bound(const u32 *OUT, u32 lo, u32 hi, long long target) {
+    int lane = threadIdx.x & 31;
+    while (hi - lo > 32) {
+        u32 step = (hi - lo + 31) / 32;
+        u64 pp = (u64)lo + (u64)step * (u32)(lane + 1);
+        u32 p = pp > hi ? hi : (u32)pp;
+        bool ge = (long long)OUT[p] >= target;
+        unsigned bal = __ballot_sync(0xffffffffu, ge);
+        int f = __ffs(bal) - 1;                                 // last probe is hi, so f >= 0
+        u64 nh = (u64)lo + (u64)step * (u32)(f + 1);
+        u32 new_hi = nh > hi ? hi : (u32)nh;
+        u32 new_lo = f == 0 ? lo : lo + step * (u32)f + 1;
+        lo = new_lo; hi = new_hi;
+    }
+    u32 p = lo + (u32)lane;
+    bool ge = p <= hi && (long long)OUT[p] >= target;
+    unsigned bal = __ballot_sync(0xffffffffu, ge);
+    return lo + (u32)(__ffs(bal) - 1);
+}
+
 __device__ u32 run_end_from(const u32 *RS, u32 W, u32 s) {      // first p > s with RS[p] != RS[s] (or W)
     u32 key = RS[s];
-    u32 lo = s + 1, hi = W;                                     // answer in [lo, hi]
+    // gallop first: runs are short in most data
+    u32 d = 1;
+    while (s + d < W && RS[s + d] == key && d < (1u << 30)) d <<= 1;
+    u32 lo = s + (d >> 1) + 1, hi = (s + d < W) ? s + d : W;    // answer in [lo, hi]
+    if (d == 1) lo = s + 1;
     while (lo < hi) {
         u32 mid = lo + (hi - lo) / 2;
         if (RS[mid] > key) hi = mid; else lo = mid + 1;
@@ -226,7 +252,8 @@ __device__ __forceinline__ u32 exit_cursor(u32 g, long long R) {
 }
 
 __global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
-    if (threadIdx.x != 0) return;
+    // all 32 lanes run the same control flow (every value is warp-uniform); lane 0 writes the results
+    const bool writer = threadIdx.x == 0;
     const u32 W = a.W, B = a.B;
     u32 s = 0, nb = 0;
     const u32 margin = a.is_eof ? 0u : 1024u;
@@ -260,14 +287,7 @@ __global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
             long long target = (long long)B - 1 - off;          // first x >= re with OUT[x] >= target
             u32 x1;
             if ((long long)a.OUT[W] < target) x1 = W + 1;       // never reached inside the window
-            else {
-                u32 lo = re, hi = W;
-                while (lo < hi) {
-                    u32 mid = lo + (hi - lo) / 2;
-                    if ((long long)a.OUT[mid] >= target) hi = mid; else lo = mid + 1;
-                }
-                x1 = lo;
-            }
+            else x1 = warp_lower_bound(a.OUT, re, W, target);
             u32 gl = NOQ;                                       // start of the last taken global group
             if (x1 <= W) {
                 // the only group that can sit exactly at the limit starts in [x1, x1+3]
@@ -331,11 +351,11 @@ __global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
         r.e = e; r.g_last = g; r.out_g = out_g;
         r.out_len = out_g + (e - g);
         if (r.out_len > a.max_out) break;                       // cannot happen for level <= 9; guards the batch stride
-        a.rec[nb++] = r;
+        if (writer) a.rec[nb] = r;
+        nb++;
         s = e;
     }
-    *a.nrec = nb;
-    *a.consumed = s;
+    if (writer) { *a.nrec = nb; *a.consumed = s; }
 }
 
 // ---------------------------------------------------------------------------------------
