@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_hist(RadixArgs a) {
 }
 
 // per block: turn per-tile digit counts into global scatter offsets (in place)
-__global__ void __launch_bounds__(256) k_radix_scan(u32 *thist, const u32 *cntp, u32 rtiles_stride) {
+static __global__ void __launch_bounds__(256) k_radix_scan(u32 *thist, const u32 *cntp, u32 rtiles_stride) {
     u32 b = blockIdx.x, d = threadIdx.x;
     u32 cnt = cntp[b];
     u32 tiles = (cnt + R_TILE - 1) / R_TILE;

@@ -405,14 +405,14 @@ __global__ void __launch_bounds__(BZ_THREADS) k_rle_emit(const u8 *x, u32 W, con
 // ---------------------------------------------------------------------------------------
 // CRC32 (crc.rs:15-22): pieces aligned to the END of each span
 // ---------------------------------------------------------------------------------------
-// spans: [s,e) from rec (block CRCs) or a single explicit span.
-__global__ void __launch_bounds__(256) k_crc_pieces(const u8 *x, const BlockRec *rec, u32 s0, u32 e0, u32 *part,
-                                                    u32 parts_stride, u32 xp /* x^(8*PIECE) */) {
+// spans[k*span_stride + 0/1] = s/e (BlockRec has them in its first two words), or one explicit span.
+__global__ void __launch_bounds__(256) k_crc_pieces(const u8 *x, const u32 *spans, u32 span_stride, u32 s0, u32 e0,
+                                                    u32 *part, u32 parts_stride, u32 xp /* x^(8*PIECE) */) {
     __shared__ u32 tab[256];
     __shared__ u32 red[256];
     make_crc_table(tab);
     u32 k = blockIdx.y;
-    u32 s = rec ? rec[k].s : s0, e = rec ? rec[k].e : e0;
+    u32 s = spans ? spans[(size_t)k * span_stride] : s0, e = spans ? spans[(size_t)k * span_stride + 1] : e0;
     u32 span = e - s;
     u32 npieces = (span + PIECE - 1) / PIECE;
     u32 p = blockIdx.x * 256 + threadIdx.x;                     // piece 0 ends at e
@@ -441,11 +441,11 @@ __global__ void __launch_bounds__(256) k_crc_pieces(const u8 *x, const BlockRec 
     if (threadIdx.x == 0 && blockIdx.x * 256 < npieces) part[(size_t)k * parts_stride + blockIdx.x] = red[0];
 }
 
-__global__ void __launch_bounds__(32) k_crc_final(const BlockRec *rec, u32 s0, u32 e0, const u32 *part,
+__global__ void __launch_bounds__(32) k_crc_final(const u32 *spans, u32 span_stride, u32 s0, u32 e0, const u32 *part,
                                                   u32 parts_stride, u32 xp256 /* x^(8*PIECE*256) */, u32 *crc_out) {
     u32 k = blockIdx.x;
     if (threadIdx.x != 0) return;
-    u32 s = rec ? rec[k].s : s0, e = rec ? rec[k].e : e0;
+    u32 s = spans ? spans[(size_t)k * span_stride] : s0, e = spans ? spans[(size_t)k * span_stride + 1] : e0;
     u32 span = e - s;
     u32 npieces = (span + PIECE - 1) / PIECE;
     u32 nparts = (npieces + 255) / 256;
@@ -527,8 +527,8 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     BZ_CHECK(ctx->d_agg2.ensure((size_t)nb * parts_stride * 4 + 64));
     u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
     dim3 gc(parts_stride, nb);
-    ctx->prof_begin(K_CRC_PIECES, 0); k_crc_pieces<<<gc, 256, 0, st>>>(d_x, rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
-    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<nb, 32, 0, st>>>(rec, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, ctx->d_crc.as<u32>()); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_PIECES, 0); k_crc_pieces<<<gc, 256, 0, st>>>(d_x, (const u32 *)rec, sizeof(BlockRec) / 4, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<nb, 32, 0, st>>>((const u32 *)rec, sizeof(BlockRec) / 4, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, ctx->d_crc.as<u32>()); LAUNCH_OK();
     B.T = ctx->d_T.as<u8>();
     B.len = ctx->d_len.as<u32>();
     return BZ2B200_OK;
@@ -543,7 +543,22 @@ int bz_crc_dev(bz2b200_ctx *ctx, const u8 *d_x, u32 n, u32 *d_crc_out) {
     BZ_CHECK(ctx->d_agg2.ensure((size_t)parts * 4 + 64));
     BZ_CHECK(cudaMemsetAsync(ctx->d_agg2.p, 0, (size_t)parts * 4, st));
     u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
-    if (n) { k_crc_pieces<<<dim3(parts, 1), 256, 0, st>>>(d_x, nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp); LAUNCH_OK(); }
-    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<1, 32, 0, st>>>(nullptr, 0, n, ctx->d_agg2.as<u32>(), parts, xp256, d_crc_out); LAUNCH_OK();
+    if (n) { ctx->prof_begin(K_CRC_PIECES, n); k_crc_pieces<<<dim3(parts, 1), 256, 0, st>>>(d_x, nullptr, 0, 0, n, ctx->d_agg2.as<u32>(), parts, xp); LAUNCH_OK(); }
+    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<1, 32, 0, st>>>(nullptr, 0, 0, n, ctx->d_agg2.as<u32>(), parts, xp256, d_crc_out); LAUNCH_OK();
+    return BZ2B200_OK;
+}
+
+// CRCs of nb spans [se[2k], se[2k+1]) of one device buffer (decoder side)
+int bz_crc_spans_dev(bz2b200_ctx *ctx, const u8 *d_x, const u32 *d_se, u32 nb, u32 max_span, u32 *d_crc_out) {
+    cudaStream_t st = ctx->stream;
+    u32 max_pieces = (max_span + PIECE - 1) / PIECE;
+    u32 parts_stride = (max_pieces + 255) / 256;
+    if (parts_stride == 0) parts_stride = 1;
+    BZ_CHECK(ctx->d_agg2.ensure((size_t)nb * parts_stride * 4 + 64));
+    BZ_CHECK(cudaMemsetAsync(ctx->d_agg2.p, 0, (size_t)nb * parts_stride * 4, st));
+    u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
+    dim3 gc(parts_stride, nb);
+    ctx->prof_begin(K_CRC_PIECES, 0); k_crc_pieces<<<gc, 256, 0, st>>>(d_x, d_se, 2, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<nb, 32, 0, st>>>(d_se, 2, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, d_crc_out); LAUNCH_OK();
     return BZ2B200_OK;
 }
