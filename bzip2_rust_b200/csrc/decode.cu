@@ -384,8 +384,9 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u64 *d_starts = ctx->d_dec3.as<u64>();
     DecBlock *d_db = (DecBlock *)(d_starts + nb);
     u32 *d_len = (u32 *)(d_db + nb);
-    u32 *d_keys = d_len + nb;
-    u64 *d_olen = (u64 *)(d_keys + nb + (nb & 1));
+    const u32 nbp = (nb + 1) & ~1u;                              // keep the u64 arrays 8-byte aligned
+    u32 *d_keys = d_len + nbp;
+    u64 *d_olen = (u64 *)(d_keys + nbp);
     u64 *d_ooff = d_olen + nb;
     u32 *d_se = (u32 *)(d_ooff + nb);
     BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
