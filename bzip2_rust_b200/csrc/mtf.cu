@@ -287,6 +287,8 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u
     if (sfreq[threadIdx.x]) atomicAdd(&freq[b * 256 + threadIdx.x], sfreq[threadIdx.x]);
 }
 
+#include "mtf_emit.cuh"   // k_mtf_emit2: the version that is launched
+
 }  // namespace
 
 #define LAUNCH_OK()                                                  \
@@ -320,7 +322,7 @@ int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, 
     ctx->prof_begin(K_USED, ne_act); k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK();
     ctx->prof_begin(K_MTF_SUMMARY, ne_act * 2); k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
     ctx->prof_begin(K_MTF_SCAN, ne_act * 2); k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
-    ctx->prof_begin(K_MTF_EMIT, ne_act * 3); k_mtf_emit<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride,
+    ctx->prof_begin(K_MTF_EMIT, ne_act * 3); k_mtf_emit2<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride,
                                            nch_stride);
     LAUNCH_OK();
     return BZ2B200_OK;
