@@ -339,14 +339,32 @@ int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, con
         int sh = (int)(pos & 7);
         uint8_t *d = out + (pos >> 3);
         const uint8_t *s = part[i];
+        if (nbytes == 0) continue;
         if (sh == 0) {
-            // last source byte may carry padding zeros only, so OR-ing whole bytes is exact
-            for (size_t j = 0; j < nbytes; j++) d[j] |= s[j];
+            // last source byte may carry padding zeros only, so OR-ing the seam byte and copying the rest is exact
+            d[0] |= s[0];
+            if (nbytes > 1) memcpy(d + 1, s + 1, nbytes - 1);
         } else {
-            for (size_t j = 0; j < nbytes; j++) {
-                d[j] |= (uint8_t)(s[j] >> sh);
-                d[j + 1] |= (uint8_t)(s[j] << (8 - sh));   // bits past `nb` are zero in the source
+            // 8 source bytes per step: big-endian 64-bit word shifted right by sh, the spill goes to the next byte
+            size_t j = 0;
+            uint8_t carry = 0;                             // low `sh` bits of the previous source byte, left aligned
+            d[0] |= (uint8_t)(s[0] >> sh);
+            carry = (uint8_t)(s[0] << (8 - sh));
+            j = 1;
+            for (; j + 8 <= nbytes; j += 8) {
+                u64 w;
+                memcpy(&w, s + j, 8);
+                w = __builtin_bswap64(w);
+                u64 o = ((u64)carry << 56) | (w >> sh);
+                carry = (uint8_t)(w << (8 - sh));
+                o = __builtin_bswap64(o);
+                memcpy(d + j, &o, 8);                      // bytes d[1..] of this part are still zero: plain stores
             }
+            for (; j < nbytes; j++) {
+                d[j] = (uint8_t)(carry | (s[j] >> sh));
+                carry = (uint8_t)(s[j] << (8 - sh));
+            }
+            d[nbytes] |= carry;                            // bits past `nb` are zero in the source
         }
         pos += nb;
     }
