@@ -6,11 +6,12 @@
 
 One "step" = one whole-stream compression of the workload:
   N = 1  : `text100m` (BASELINE config 2: 100 MB synthetic text-like corpus, level 9)
-  N > 1  : one stream of N x 100 MB, blocks dealt to the GPUs in contiguous ranges, no data-path
-           collective (blocks never exchange data), ordered merge on rank 0          -> "weak" scaling
-`value`  : input and output resident in HBM (bz2b200_compress_stream_dev / _range_dev)
-`e2e`    : the same through the host-pointer C ABI (bz2b200_compress_stream): pinned host input,
-           H2D + kernels + D2H of the .bz2 bytes inside the timed region
+  N > 1  : ONE stream of N x 100 MB; rank r compresses the blocks that start in its 100 MB slice.  The block
+           chain is handed from rank to rank as one number (no data-path collective: blocks never exchange
+           data); the ordered merge ORs pre-shifted bit strings on rank 0.                     -> "weak" scaling
+`value`  : input and output resident in HBM (bz2b200_compress_stream_dev / bz2b200_shard_*_dev)
+`e2e`    : the same through host buffers: pinned host input, H2D + kernels + D2H of the .bz2 bytes (and, for
+           N > 1, the gather + merge + final D2H) inside the timed region
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -65,23 +66,30 @@ class ClockSampler:
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                  "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            return
+        self._p = p
+        for line in p.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+            if self._stop.is_set():
+                break
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+        time.sleep(0.3)
 
     def stop(self):
         self._stop.set()
+        try:
+            self._p.terminate()
+        except Exception:
+            pass
         if self._t:
-            self._t.join(timeout=6)
+            self._t.join(timeout=3)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -163,7 +171,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        gloo = dist.new_group(backend="gloo")
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local if world > 1 else 0)
@@ -189,9 +196,15 @@ def main():
 
     eng = bz.Engine(local if world > 1 else 0)
     L = bz.load_library()
-    cap = int(L.bz2b200_compress_bound(total))
+    my_lo, my_hi = rank * per, (total if rank == world - 1 else (rank + 1) * per)
+    cap = int(L.bz2b200_compress_bound(total if world == 1 else per + (64 << 20)))
     d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
-    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(int(L.bz2b200_compress_bound(total)), dtype=torch.uint8).pin_memory()
+    if world > 1:
+        d_shift = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
+        win_cap = min(total - my_lo, per + (64 << 20))
+        d_win = torch.empty(win_cap, dtype=torch.uint8, device=dev)
+        d_final = torch.empty(h_out.numel(), dtype=torch.uint8, device=dev) if rank == 0 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -199,73 +212,107 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def my_range(starts):
-        nb = len(starts) - 1
-        first = rank * nb // world
-        last = (rank + 1) * nb // world
-        return first, last - first
-
     out_len = C.c_size_t()
     state = {}
 
+    def chain_recv():
+        if rank == 0:
+            return 0
+        t = torch.zeros(1, dtype=torch.int64, device=dev)
+        dist.recv(t, rank - 1)
+        return int(t.item())
+
+    def chain_send(nxt):
+        if rank < world - 1:
+            dist.send(torch.tensor([nxt], dtype=torch.int64, device=dev), rank + 1)
+
     def step_dev():
-        """HBM-resident: plan (replicated) + this rank's block range."""
+        """HBM-resident.  N > 1: scan own slice, take the chain from rank-1, pass it on, compress own blocks."""
         if world == 1:
-            n = eng.compress_dev(d_in.data_ptr(), total, level, d_out.data_ptr(), cap)
-            state["dev_len"] = n
-        else:
-            starts = eng.stream_plan(total, level, dev_ptr=d_in.data_ptr())
-            first, count = my_range(starts)
-            _, bits, crcs = eng.compress_range(total, level, starts, first, count, dev_ptr=d_in.data_ptr(),
-                                               dev_out=d_out.data_ptr(), dev_out_cap=cap)
-            state["dev_bits"] = bits
+            state["dev_len"] = eng.compress_dev(d_in.data_ptr(), total, level, d_out.data_ptr(), cap)
+            return
+        start = chain_recv()
+        nxt, nb = eng.shard_plan(d_in.data_ptr(), 0, total, total, level, start, my_hi)
+        chain_send(nxt)
+        bits, crcs = eng.shard_compress(nb, d_out.data_ptr(), cap)
+        state["dev_bits"], state["dev_crcs"] = bits, crcs
 
     def step_e2e():
-        """Host buffers through the C ABI; copies inside the timed region.  -> (h2d bytes, d2h bytes)"""
+        """Host buffers; copies inside the timed region.  -> (h2d bytes, d2h bytes) of this rank"""
         if world == 1:
-            rc = L.bz2b200_compress_stream(eng._h, h_in.data_ptr(), total, level, h_out.data_ptr(), cap, C.byref(out_len))
+            rc = L.bz2b200_compress_stream(eng._h, h_in.data_ptr(), total, level, h_out.data_ptr(), h_out.numel(),
+                                           C.byref(out_len))
             if rc != 0:
                 raise RuntimeError("compress_stream failed: %d %s" % (rc, L.bz2b200_last_error(eng._h)))
             return total, out_len.value
-        # rank 0 plans and broadcasts the block starts; every rank uploads only its own range
-        nmax = total // (level * 100000 - 27) + 8
-        st = torch.zeros(nmax + 2, dtype=torch.int64)
-        h2d = 0
+        # upload own slice (+ look-ahead for the last block, grown on demand) while the chain arrives
+        look = 2 << 20
+        win_len = min(total - my_lo, (my_hi - my_lo) + look)
+        d_win[:win_len].copy_(h_in[my_lo:my_lo + win_len], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d = win_len
+        start = chain_recv()
+        while True:
+            try:
+                nxt, nb = eng.shard_plan(d_win.data_ptr(), my_lo, win_len, total, level, start, my_hi)
+                break
+            except bz.Bz2B200Error as e:
+                if e.rc != bz.E_CAP or win_len >= min(total - my_lo, d_win.numel()):
+                    raise
+                new_len = min(total - my_lo, d_win.numel(), win_len + 8 * look)
+                d_win[win_len:new_len].copy_(h_in[my_lo + win_len:my_lo + new_len], non_blocking=True)
+                torch.cuda.synchronize()
+                h2d += new_len - win_len
+                win_len = new_len
+        chain_send(nxt)
+        bits, crcs = eng.shard_compress(nb, d_out.data_ptr(), cap)
+        # ordered merge: exchange bit lengths, shift to the final bit phase on the device, gather, OR on rank 0
+        meta = torch.tensor([bits, nb], dtype=torch.int64, device=dev)
+        metas = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        metas = [m.tolist() for m in metas]
+        offs, pos = [], 32
+        for b_r, _ in metas:
+            offs.append(pos)
+            pos += b_r
+        phase = offs[rank] % 8
+        eng.shift_bits(d_out.data_ptr(), bits, phase, d_shift.data_ptr())
+        nbytes = (bits + phase + 7) // 8
+        maxbytes = max((b_r + 7 + 7) // 8 for b_r, _ in metas) + 8
+        maxcrc = max(n_r for _, n_r in metas) + 1
+        part = d_shift[:maxbytes]
+        crc_t = torch.zeros(maxcrc, dtype=torch.int64, device=dev)
+        crc_t[:nb] = torch.from_numpy(crcs.astype(np.int64)).to(dev)
         if rank == 0:
-            starts = eng.stream_plan(h_in.numpy(), level)
-            st[0] = len(starts)
-            st[1:1 + len(starts)] = torch.from_numpy(starts.astype(np.int64))
-            h2d += total
-        dist.broadcast(st, 0, group=gloo)
-        starts = st[1:1 + int(st[0])].numpy().astype(np.uint64)
-        first, count = my_range(starts)
-        nblocks = len(starts) - 1
-        crcs = np.zeros(max(count, 1), dtype=np.uint32)
-        bits = C.c_uint64()
-        rc = L.bz2b200_compress_range(eng._h, h_in.data_ptr(), total, level, starts.ctypes.data, nblocks, first, count,
-                                      h_out.data_ptr(), cap, C.byref(bits), crcs.ctypes.data)
-        if rc != 0:
-            raise RuntimeError("compress_range failed: %d %s" % (rc, L.bz2b200_last_error(eng._h)))
-        nbytes = (bits.value + 7) // 8
-        h2d += int(starts[first + count] - starts[first])
-        # ordered merge on rank 0 (host side): gather sizes, then the bit strings and block CRCs
-        meta = torch.tensor([bits.value, count], dtype=torch.int64)
-        metas = [torch.zeros(2, dtype=torch.int64) for _ in range(world)] if rank == 0 else None
-        dist.gather(meta, metas, 0, group=gloo)
-        if rank == 0:
-            bufs = [(h_out[:nbytes].numpy().tobytes(), bits.value, list(crcs[:count]))]
-            for r in range(1, world):
-                nb_r = (int(metas[r][0]) + 7) // 8
-                t = torch.empty(nb_r, dtype=torch.uint8)
-                c = torch.empty(int(metas[r][1]), dtype=torch.int64)
-                dist.recv(t, r, group=gloo)
-                dist.recv(c, r, group=gloo)
-                bufs.append((t.numpy().tobytes(), int(metas[r][0]), [int(x) for x in c]))
-            state["merged"] = bz.merge_streams(level, bufs)
-        else:
-            dist.send(h_out[:nbytes].clone(), 0, group=gloo)
-            dist.send(torch.from_numpy(crcs[:count].astype(np.int64)), 0, group=gloo)
-        return h2d, nbytes
+            gp = [torch.empty(maxbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+            gc_ = [torch.empty(maxcrc, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.gather(part, gp, 0)
+            dist.gather(crc_t, gc_, 0)
+            total_bits = pos + 80
+            nfinal = (total_bits + 7) // 8
+            d_final[:nfinal + 8].zero_()
+            combined = 0
+            for r in range(world):
+                b_r, n_r = metas[r]
+                nby = (b_r + offs[r] % 8 + 7) // 8
+                lo = offs[r] // 8
+                d_final[lo:lo + nby].bitwise_or_(gp[r][:nby])
+                for cval in gc_[r][:n_r].tolist():
+                    combined = (((combined << 1) | (combined >> 31)) & 0xFFFFFFFF) ^ cval      # crc.rs:25-27
+            h_out[:nfinal].copy_(d_final[:nfinal])
+            torch.cuda.synchronize()
+            buf = h_out.numpy()
+            buf[0:4] = np.frombuffer(b"BZh" + bytes([48 + level]), dtype=np.uint8)                # bitwriter.rs:67-72
+            foot = ((0x177245385090 << 32) | combined) << ((8 - total_bits % 8) % 8)                # bitwriter.rs:103-114
+            fb = foot.to_bytes(11, "big")
+            tail = np.frombuffer(fb, dtype=np.uint8)
+            fstart = nfinal - 11
+            buf[fstart:nfinal] |= tail
+            state["merged_len"] = nfinal
+            return h2d, nfinal
+        dist.gather(part, None, 0)
+        dist.gather(crc_t, None, 0)
+        return h2d, 0
 
     # ---- warm-up ----
     eng.set_timing(2)
@@ -277,8 +324,8 @@ def main():
 
     # ---- timed: HBM-resident value ----
     sampler = ClockSampler(local if world > 1 else 0)
-    barrier()
     sampler.start()
+    barrier()
     launches0 = eng.launches
     t0 = time.perf_counter()
     dev_ms = []
@@ -297,7 +344,7 @@ def main():
     dt_max = float(tt.item())
     value = total / 1e6 * args.steps / dt_max
 
-    # ---- timed: end to end through the host-pointer C ABI ----
+    # ---- timed: end to end through host buffers ----
     eng.set_timing(1)
     barrier()
     t0 = time.perf_counter()
@@ -308,9 +355,12 @@ def main():
     barrier()
     clocks = sampler.stop()
     tt = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    hb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hb, op=dist.ReduceOp.SUM)
     e2e_value = total / 1e6 * args.steps / float(tt.item())
+    h2d_total, d2h_total = [int(x) for x in hb.tolist()]
 
     # ---- verification outside the timed region: libbz2 round trip of the produced stream ----
     verified = None
@@ -320,8 +370,16 @@ def main():
             stream = h_out[:out_len.value].numpy().tobytes()
             dev_stream = d_out[:state["dev_len"]].cpu().numpy().tobytes()
             verified = (stream == dev_stream) and (bz2.decompress(stream) == h_in.numpy().tobytes())
+            clen = out_len.value
         else:
-            verified = bz2.decompress(state["merged"]) == h_in.numpy().tobytes()
+            stream = h_out[:state["merged_len"]].numpy().tobytes()
+            verified = bz2.decompress(stream) == h_in.numpy().tobytes()
+            # and the sharded stream is the same bytes one GPU produces for the whole input
+            one = eng.compress(h_in.numpy(), level)
+            verified = verified and (one == stream)
+            clen = state["merged_len"]
+    else:
+        clen = out_len.value if world == 1 else state.get("merged_len", 0)
 
     if rank != 0:
         if world > 1:
@@ -360,8 +418,8 @@ def main():
                                                                             " x%d as one stream, blocks sharded" % world),
                    "level": level, "input_bytes_per_gpu": per, "input_bytes_total": total,
                    "l2": "inputs + workspaces (>4 GB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": "blocks x%d, no collective" % world},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                   "parallelism": "blocks x%d, no collective on the data path" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -373,7 +431,7 @@ def main():
         "top_kernels": [{"kernel": k, "ms": v[0] / args.steps, "launches": v[1] // args.steps,
                          "GBps_algorithmic": (v[2] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else 0.0} for k, v in top],
         "verified_roundtrip_libbz2": verified,
-        "compressed_bytes": int(out_len.value) if world == 1 else len(state.get("merged", b"")),
+        "compressed_bytes": int(clen),
     }
     print(json.dumps(line))
     if world > 1:

@@ -36,6 +36,7 @@ EXPORTS = [
     "bz2b200_mtf_rle2", "bz2b200_huffman", "bz2b200_bwt_decode", "bz2b200_decompress_stream",
     "bz2b200_set_timing", "bz2b200_get_timing", "bz2b200_get_bwt_stats", "bz2b200_kernel_stats",
     "bz2b200_reset_kernel_stats", "bz2b200_stream_plan_dev", "bz2b200_compress_range_dev",
+    "bz2b200_shard_plan_dev", "bz2b200_shard_compress_dev", "bz2b200_shift_bits_dev",
 ]
 
 
@@ -76,6 +77,10 @@ def load_library():
                                          u8p, C.c_size_t, C.POINTER(C.c_uint64), u32p]
     L.bz2b200_stream_plan_dev.argtypes = L.bz2b200_stream_plan.argtypes
     L.bz2b200_compress_range_dev.argtypes = L.bz2b200_compress_range.argtypes
+    L.bz2b200_shard_plan_dev.argtypes = [vp, u8p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
+                                         szp, C.POINTER(C.c_uint32)]
+    L.bz2b200_shard_compress_dev.argtypes = [vp, u8p, C.c_size_t, C.POINTER(C.c_uint64), u32p]
+    L.bz2b200_shift_bits_dev.argtypes = [vp, u8p, C.c_uint64, C.c_int, u8p]
     L.bz2b200_merge_streams.argtypes = [C.c_int, C.c_int, vp, u64p, vp, u32p, u8p, C.c_size_t, szp]
     L.bz2b200_crc32.argtypes = [vp, u8p, C.c_size_t, C.POINTER(C.c_uint32)]
     L.bz2b200_rle1_split.argtypes = [vp, u8p, C.c_size_t, C.c_int, u8p, C.c_size_t, u64p, u64p, u32p,
@@ -288,6 +293,23 @@ class Engine:
         self._chk(self._L.bz2b200_compress_range(self._h, a.ctypes.data, a.size, level, starts.ctypes.data, nblocks,
                                                  first, count, out.ctypes.data, cap, C.byref(bits), crcs.ctypes.data))
         return out[:(bits.value + 7) // 8].tobytes(), int(bits.value), crcs[:count].copy()
+
+    def shard_plan(self, d_win_ptr, win_lo, win_len, n_total, level, start, stop_at):
+        """Plans the blocks starting in [start, stop_at) -> (next_start, nblocks); raises E_CAP if the window is short."""
+        nxt, nb = C.c_size_t(), C.c_uint32()
+        self._chk(self._L.bz2b200_shard_plan_dev(self._h, d_win_ptr, win_lo, win_len, n_total, level, start, stop_at,
+                                                 C.byref(nxt), C.byref(nb)))
+        return nxt.value, nb.value
+
+    def shard_compress(self, nblocks, d_out_ptr, out_cap):
+        """Compresses the blocks of the preceding shard_plan -> (nbits, crcs)."""
+        crcs = np.zeros(max(nblocks, 1), dtype=np.uint32)
+        bits = C.c_uint64()
+        self._chk(self._L.bz2b200_shard_compress_dev(self._h, d_out_ptr, out_cap, C.byref(bits), crcs.ctypes.data))
+        return int(bits.value), crcs[:nblocks].copy()
+
+    def shift_bits(self, d_src_ptr, nbits, phase, d_dst_ptr):
+        self._chk(self._L.bz2b200_shift_bits_dev(self._h, d_src_ptr, nbits, phase, d_dst_ptr))
 
     def bwt_decode(self, key, bwt):
         a = _np_u8(bwt)

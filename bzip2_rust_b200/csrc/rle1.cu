@@ -200,6 +200,7 @@ struct ChainArgs {
     u32 is_eof;       // window ends at the end of the stream
     u32 max_blocks;
     u32 max_out;      // largest RLE1 block the batch stride can hold
+    u32 stop_at;      // stop the chain at the first block start >= stop_at (shard end), window relative
     u32 off_from;     // EOF bookkeeping: a group starting at/after this position since the last refill puts the
                       // reference's `remaining` counter one high (rle1.rs:207) -- see DESIGN.md "EOF corner"
     BlockRec *rec; u32 *nrec; u32 *consumed;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
     const u32 W = a.W, B = a.B;
     u32 s = 0, nb = 0;
     const u32 margin = a.is_eof ? 0u : 1024u;
-    while (s < W && nb < a.max_blocks) {
+    while (s < W && s < a.stop_at && nb < a.max_blocks) {
         BlockRec r;
         r.s = s; r.last = 0;
         // ---- first run, parsed from s ----
@@ -469,7 +470,8 @@ __global__ void __launch_bounds__(32) k_crc_final(const u32 *spans, u32 span_str
 // On return: *nblocks blocks were written into the context's batch text array (ctx->d_T, ctx->d_len,
 // ctx->d_crc), `B` describes them, *consumed = input bytes covered.  h_rec (optional) receives the records.
 int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eof, u32 off_from, u32 max_blocks,
-                   Batch &B, u32 *nblocks, u32 *consumed, std::vector<u32> *h_spans, bool plan_only) {
+                   Batch &B, u32 *nblocks, u32 *consumed, std::vector<u32> *h_spans, bool plan_only, u32 stop_at,
+                   bool reuse_plan) {
     cudaStream_t st = ctx->stream;
     u32 Bsz = (u32)level * 100000u - 19u;
     u32 max_n = Bsz + 8;                                        // RLE1 block length <= B + 5
@@ -486,7 +488,9 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     u32 *d_small = (u32 *)(rec + max_blocks);                   // [0]=nrec [1]=consumed
     BZ_CHECK(ctx->h_small.ensure(64 + (size_t)max_blocks * sizeof(BlockRec)));
 
-    if (W > 0) {
+    // reuse_plan: the scans and the chain of the immediately preceding plan-only call on the same window are
+    // still in d_runflag / d_misc (bz2b200_shard_plan_dev -> bz2b200_shard_compress_dev)
+    if (!reuse_plan && W > 0) {
         ctx->prof_begin(K_RS_AGG, (u64)W); k_rs_agg<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1); LAUNCH_OK();
         ctx->prof_begin(K_FLAT_SCAN, (u64)tiles * 32); k_flat_scan<<<1, 256, 0, st>>>(tagg1, tiles, nullptr); LAUNCH_OK();
         ctx->prof_begin(K_RS_APPLY, (u64)W * 5); k_rs_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1, RS, tagg2); LAUNCH_OK();
@@ -495,9 +499,9 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     }
     ChainArgs a;
     a.x = d_x; a.RS = RS; a.OUT = OUT; a.LASTQ = LASTQ; a.W = W; a.B = Bsz; a.is_eof = is_eof ? 1u : 0u;
-    a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from;
+    a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from; a.stop_at = stop_at;
     a.rec = rec; a.nrec = d_small; a.consumed = d_small + 1;
-    ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK();
+    if (!reuse_plan) { ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK(); }
     u32 *hs = ctx->h_small.as<u32>();
     BZ_CHECK(cudaMemcpyAsync(hs, d_small, 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));

@@ -1,0 +1,143 @@
+// shard.cu -- multi-GPU sharding of ONE stream without replicating the block plan.
+//
+// The block chain s_{k+1} = e(s_k) is sequential over the whole input (rle1.rs:245-264 is an iterator),
+// but each link only needs the per-position arrays around it.  So every rank scans its own slice in
+// parallel, and the chain is handed from rank to rank as ONE number:
+//     rank r:  start_r  = (r == 0) ? 0 : recv(r-1)
+//              plan blocks whose start lies in [start_r, stop_r)        (bz2b200_shard_plan_dev)
+//              send(next_start) to r+1                                    -- before the heavy work
+//              compress the planned blocks                                (bz2b200_shard_compress_dev)
+// The ranks' bit strings are then shifted to their final bit phase on the device (bz2b200_shift_bits_dev) so
+// that the ordered merge is a byte copy with an OR on the seam byte.
+#include "common.cuh"
+#include <algorithm>
+#include <string.h>
+
+u32 off_from_for(size_t n, int level, size_t window_pos);
+int bz_concat_blocks(bz2b200_ctx *ctx, const HufOut &H, u32 nb, const u64 *hoff, u64 maxbits, u8 *d_out);
+int bz_shift_bits(bz2b200_ctx *ctx, const u8 *d_src, u64 nbits, int phase, u8 *d_dst);
+
+namespace {
+struct ShardPlan {
+    bool valid = false;
+    const u8 *d_win = nullptr;
+    u32 W = 0; int level = 0; bool eof = false; u32 off_from = 0; u32 max_blocks = 0; u32 stop_at = 0;
+    u32 nb = 0;
+};
+// one pending plan per context (keyed by the context pointer; contexts are few)
+std::mutex g_mu;
+std::vector<std::pair<bz2b200_ctx *, ShardPlan>> g_plans;
+ShardPlan &plan_of(bz2b200_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &p : g_plans) if (p.first == ctx) return p.second;
+    g_plans.emplace_back(ctx, ShardPlan());
+    return g_plans.back().second;
+}
+constexpr u32 MAX_SHARD_BLOCKS = 4096;
+}  // namespace
+
+extern "C" {
+
+// d_win[0 .. win_len) = bytes [win_lo, win_lo + win_len) of a stream of n_total bytes, on this context's GPU.
+// Plans every block whose first byte lies in [start, stop_at) (absolute offsets; `start` must be a true block
+// start inside the window).  *next_start = first block start >= stop_at (or n_total).  Returns
+// BZ2B200_E_CAP if the window ends before the last such block does (upload more and call again).
+int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
+                           int level, size_t start, size_t stop_at, size_t *next_start, uint32_t *nblocks) {
+    if (!ctx || !d_win || !next_start || !nblocks || level < 1 || level > 9 || start < win_lo ||
+        start > win_lo + win_len || win_lo + win_len > n_total || win_len > 0xFFFFFF00ull)
+        return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    ShardPlan &P = plan_of(ctx);
+    P.valid = false;
+    *nblocks = 0;
+    if (start >= stop_at || start >= n_total) { *next_start = start; P.nb = 0; P.valid = true; P.d_win = nullptr; return BZ2B200_OK; }
+    const u8 *x = d_win + (start - win_lo);
+    u32 W = (u32)(win_lo + win_len - start);
+    bool eof = win_lo + win_len == n_total;
+    u32 stop_rel = (u32)std::min<size_t>(stop_at - start, 0xFFFFFFF0u);
+    Batch B; u32 nb = 0, consumed = 0;
+    u32 off_from = off_from_for(n_total, level, start);
+    int rc = bz_rle1_window(ctx, x, W, level, eof, off_from, MAX_SHARD_BLOCKS, B, &nb, &consumed, nullptr, true, stop_rel, false);
+    if (rc) return rc;
+    // the chain stopped early if it ran out of window before reaching stop_at
+    if (consumed < stop_rel && !(eof && consumed == W)) return BZ2B200_E_CAP;
+    *next_start = start + consumed;
+    *nblocks = nb;
+    P.valid = true; P.d_win = x; P.W = W; P.level = level; P.eof = eof; P.off_from = off_from;
+    P.max_blocks = MAX_SHARD_BLOCKS; P.stop_at = stop_rel; P.nb = nb;
+    return BZ2B200_OK;
+}
+
+// Compresses the blocks of the preceding bz2b200_shard_plan_dev call (same context, window still resident).
+// d_out receives one bit string (no stream header/footer); block_crcs[nblocks].
+int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
+                               uint32_t *block_crcs) {
+    if (!ctx || !d_out || !out_bits) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    ShardPlan &P = plan_of(ctx);
+    if (!P.valid) { ctx->err = "shard_compress: no pending plan"; return BZ2B200_E_ARG; }
+    P.valid = false;
+    *out_bits = 0;
+    cudaStream_t st = ctx->stream;
+    if (ctx->timing) cudaEventRecord(ctx->ev_total[0], st);
+    BZ_CHECK(cudaMemsetAsync(d_out, 0, out_cap & ~(size_t)3, st));
+    if (P.nb == 0) return BZ2B200_OK;
+    if (!block_crcs) return BZ2B200_E_ARG;
+    Batch B; u32 nb = 0, consumed = 0;
+    int rc = bz_rle1_window(ctx, P.d_win, P.W, P.level, P.eof, P.off_from, P.max_blocks, B, &nb, &consumed, nullptr, false,
+                            P.stop_at, true);
+    if (rc) return rc;
+    if (nb != P.nb) { ctx->err = "shard_compress: plan changed"; return BZ2B200_E_ARG; }
+    // the BWT workspace is sized per batch; a shard is compressed in sub-batches of whole blocks
+    u32 stride = B.stride;
+    u32 batch_blocks = (u32)std::max<size_t>(1, ((size_t)272 << 20) / stride);
+    u64 bitpos = 0;
+    std::vector<u64> hoff;
+    for (u32 first = 0; first < nb; first += batch_blocks) {
+        u32 cnt = std::min(batch_blocks, nb - first);
+        Batch S = B;
+        S.nblk = (int)cnt;
+        S.T = B.T + (size_t)first * stride;
+        S.len = B.len + first;
+        S.total_n = B.total_n * cnt / nb;
+        HufOut H;
+        rc = bz_compress_batch(ctx, S, ctx->d_crc.as<u32>() + first, H);
+        if (rc) return rc;
+        BZ_CHECK(ctx->h_small.ensure((size_t)cnt * 12 + 64));
+        u64 *hbits = ctx->h_small.as<u64>();
+        u32 *hcrc = (u32 *)(hbits + cnt);
+        BZ_CHECK(cudaMemcpyAsync(hbits, H.d_bits, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        BZ_CHECK(cudaMemcpyAsync(hcrc, ctx->d_crc.as<u32>() + first, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        BZ_CHECK(cudaStreamSynchronize(st));
+        hoff.resize(cnt);
+        u64 maxbits = 0;
+        for (u32 k = 0; k < cnt; k++) {
+            hoff[k] = bitpos; bitpos += hbits[k]; maxbits = std::max(maxbits, hbits[k]);
+            block_crcs[first + k] = hcrc[k];
+        }
+        if ((bitpos + 7) / 8 + 16 > out_cap) return BZ2B200_E_CAP;
+        rc = bz_concat_blocks(ctx, H, cnt, hoff.data(), maxbits, d_out);
+        if (rc) return rc;
+    }
+    if (ctx->timing) {
+        cudaEventRecord(ctx->ev_total[1], st);
+        cudaEventSynchronize(ctx->ev_total[1]);
+        cudaEventElapsedTime(&ctx->stage_ms[5], ctx->ev_total[0], ctx->ev_total[1]);
+    }
+    *out_bits = bitpos;
+    return BZ2B200_OK;
+}
+
+// d_dst = d_src shifted right by `phase` bits (0..7): byte k of d_dst then lines up with byte (offset/8 + k)
+// of the final stream when phase = offset % 8.  d_dst needs (nbits + phase + 7)/8 + 8 bytes.
+int bz2b200_shift_bits_dev(bz2b200_ctx *ctx, const uint8_t *d_src, uint64_t nbits, int phase, uint8_t *d_dst) {
+    if (!ctx || !d_src || !d_dst || phase < 0 || phase > 7) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    return bz_shift_bits(ctx, d_src, nbits, phase, d_dst);
+}
+
+}  // extern "C"

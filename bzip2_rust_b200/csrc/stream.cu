@@ -69,7 +69,37 @@ constexpr size_t MAX_BATCH_BYTES = 272u << 20;   // RLE1 bytes per BWT batch (wo
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
 
-static u32 off_from_for(size_t n, int level, size_t window_pos) {
+// OR nb packed blocks (H) into d_out at the absolute bit offsets hoff[] (host array); synchronises the stream.
+int bz_concat_blocks(bz2b200_ctx *ctx, const HufOut &H, u32 nb, const u64 *hoff, u64 maxbits, u8 *d_out) {
+    cudaStream_t st = ctx->stream;
+    BZ_CHECK(ctx->d_bitoff.ensure((size_t)nb * 8));
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_bitoff.p, hoff, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+    dim3 gc((u32)(((maxbits + 31) / 32 + 255) / 256), nb);
+    ctx->prof_begin(K_CONCAT, maxbits / 4 * nb);
+    k_concat_bits<<<gc, 256, 0, st>>>(H.d_out, H.out_stride, H.d_bits, ctx->d_bitoff.as<u64>(), (u32 *)d_out);
+    LAUNCH_OK();
+    BZ_CHECK(cudaStreamSynchronize(st));
+    return BZ2B200_OK;
+}
+// dst = src shifted right by `phase` bits (0..7); dst must hold (nbits + phase + 7) / 8 + 8 zeroed-able bytes
+int bz_shift_bits(bz2b200_ctx *ctx, const u8 *d_src, u64 nbits, int phase, u8 *d_dst) {
+    cudaStream_t st = ctx->stream;
+    size_t dst_bytes = (size_t)((nbits + phase + 7) / 8);
+    BZ_CHECK(cudaMemsetAsync(d_dst, 0, (dst_bytes + 7) & ~(size_t)3, st));
+    BZ_CHECK(ctx->d_bitoff.ensure(16));
+    u64 h[2] = {nbits, (u64)phase};
+    BZ_CHECK(cudaMemcpyAsync(ctx->d_bitoff.p, h, 16, cudaMemcpyHostToDevice, st));
+    dim3 gc((u32)(((nbits + 31) / 32 + 255) / 256), 1);
+    if (nbits) {
+        ctx->prof_begin(K_CONCAT, nbits / 4);
+        k_concat_bits<<<gc, 256, 0, st>>>(d_src, 0, ctx->d_bitoff.as<u64>(), ctx->d_bitoff.as<u64>() + 1, (u32 *)d_dst);
+        LAUNCH_OK();
+    }
+    BZ_CHECK(cudaStreamSynchronize(st));
+    return BZ2B200_OK;
+}
+
+u32 off_from_for(size_t n, int level, size_t window_pos) {
     // Position (window relative) after which a group leaves the reference's `remaining` counter one high at EOF:
     // the last short read happens when fewer than 260 bytes are left of the last full read (rle1.rs:63-85,:143).
     size_t Bsz = (size_t)level * 100000 - 19;

@@ -86,6 +86,18 @@ int bz2b200_compress_range_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, 
                                const uint64_t *block_start, uint32_t nblocks_total,
                                uint32_t first, uint32_t count,
                                uint8_t *d_out, size_t out_cap, uint64_t *out_bits, uint32_t *block_crcs);
+/* Sharded planning without replicating the plan: the chain of block starts (rle1.rs:245-264 is a serial
+ * iterator) is handed from rank to rank as one number.  d_win = bytes [win_lo, win_lo+win_len) of the stream on
+ * this GPU.  Plans the blocks starting in [start, stop_at); *next_start is what the next rank starts from.
+ * BZ2B200_E_CAP = the window ends before the last such block does (make the window longer and call again).
+ * bz2b200_shard_compress_dev then compresses exactly those blocks (window must still be resident). */
+int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
+                           int level, size_t start, size_t stop_at, size_t *next_start, uint32_t *nblocks);
+int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
+                               uint32_t *block_crcs);
+/* d_dst = d_src shifted right by phase (0..7) bits, so a rank can pre-align its bit string to its final offset
+ * and the ordered merge becomes a byte copy with an OR on the seam byte. */
+int bz2b200_shift_bits_dev(bz2b200_ctx *ctx, const uint8_t *d_src, uint64_t nbits, int phase, uint8_t *d_dst);
 /* Ordered concatenation at bit granularity + "BZh<level>" header + footer with combined CRC
  * (bitwriter.rs:67-72, :89-114; crc.rs:25-27).  Pure host code. */
 int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, const uint64_t *part_bits,
