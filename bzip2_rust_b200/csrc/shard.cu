@@ -44,15 +44,18 @@ extern "C" {
 // BZ2B200_E_CAP if the window ends before the last such block does (upload more and call again).
 int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
                            int level, size_t start, size_t stop_at, size_t *next_start, uint32_t *nblocks) {
-    if (!ctx || !d_win || !next_start || !nblocks || level < 1 || level > 9 || start < win_lo ||
-        start > win_lo + win_len || win_lo + win_len > n_total || win_len > 0xFFFFFF00ull)
+    if (!ctx || !d_win || !next_start || !nblocks || level < 1 || level > 9 || win_lo + win_len > n_total ||
+        win_len > 0xFFFFFF00ull)
         return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     ShardPlan &P = plan_of(ctx);
     P.valid = false;
     *nblocks = 0;
+    // the previous rank's last block may already cover this whole shard: nothing to do, pass the chain on
     if (start >= stop_at || start >= n_total) { *next_start = start; P.nb = 0; P.valid = true; P.d_win = nullptr; return BZ2B200_OK; }
+    if (start < win_lo) return BZ2B200_E_ARG;
+    if (start >= win_lo + win_len) return BZ2B200_E_CAP;          // window does not reach the first block yet
     const u8 *x = d_win + (start - win_lo);
     u32 W = (u32)(win_lo + win_len - start);
     bool eof = win_lo + win_len == n_total;
