@@ -156,6 +156,16 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # Only the JSON line may reach stdout: NCCL / torchrun chatter written to fd 1 goes to stderr instead.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _main(args, real_stdout)
+    finally:
+        os.dup2(real_stdout, 1)
+
+
+def _main(args, real_stdout):
 
     import torch
     import bzip2_rust_b200 as bz
@@ -224,15 +234,18 @@ def main():
 
     def chain_send(nxt):
         if rank < world - 1:
-            dist.send(torch.tensor([nxt], dtype=torch.int64, device=dev), rank + 1)
+            state["chain_t"] = torch.tensor([nxt], dtype=torch.int64, device=dev)      # keep alive until sent
+            dist.send(state["chain_t"], rank + 1)
 
     def step_dev():
         """HBM-resident.  N > 1: scan own slice, take the chain from rank-1, pass it on, compress own blocks."""
         if world == 1:
             state["dev_len"] = eng.compress_dev(d_in.data_ptr(), total, level, d_out.data_ptr(), cap)
             return
+        win_hi = min(total, my_hi + (64 << 20))                # look-ahead for the last block of the slice
+        eng.shard_scan(d_in.data_ptr() + my_lo, my_lo, win_hi - my_lo, total, level)     # parallel on all ranks
         start = chain_recv()
-        nxt, nb = eng.shard_plan(d_in.data_ptr(), 0, total, total, level, start, my_hi)
+        nxt, nb = eng.shard_plan(d_in.data_ptr() + my_lo, my_lo, win_hi - my_lo, total, level, start, my_hi)
         chain_send(nxt)
         bits, crcs = eng.shard_compress(nb, d_out.data_ptr(), cap)
         state["dev_bits"], state["dev_crcs"] = bits, crcs
@@ -251,6 +264,7 @@ def main():
         d_win[:win_len].copy_(h_in[my_lo:my_lo + win_len], non_blocking=True)
         torch.cuda.synchronize()
         h2d = win_len
+        eng.shard_scan(d_win.data_ptr(), my_lo, win_len, total, level)
         start = chain_recv()
         while True:
             try:
@@ -433,7 +447,7 @@ def main():
         "verified_roundtrip_libbz2": verified,
         "compressed_bytes": int(clen),
     }
-    print(json.dumps(line))
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

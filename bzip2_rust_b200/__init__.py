@@ -36,7 +36,7 @@ EXPORTS = [
     "bz2b200_mtf_rle2", "bz2b200_huffman", "bz2b200_bwt_decode", "bz2b200_decompress_stream",
     "bz2b200_set_timing", "bz2b200_get_timing", "bz2b200_get_bwt_stats", "bz2b200_kernel_stats",
     "bz2b200_reset_kernel_stats", "bz2b200_stream_plan_dev", "bz2b200_compress_range_dev",
-    "bz2b200_shard_plan_dev", "bz2b200_shard_compress_dev", "bz2b200_shift_bits_dev",
+    "bz2b200_shard_plan_dev", "bz2b200_shard_compress_dev", "bz2b200_shift_bits_dev", "bz2b200_shard_scan_dev",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library():
     L.bz2b200_compress_range_dev.argtypes = L.bz2b200_compress_range.argtypes
     L.bz2b200_shard_plan_dev.argtypes = [vp, u8p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
                                          szp, C.POINTER(C.c_uint32)]
+    L.bz2b200_shard_scan_dev.argtypes = [vp, u8p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
     L.bz2b200_shard_compress_dev.argtypes = [vp, u8p, C.c_size_t, C.POINTER(C.c_uint64), u32p]
     L.bz2b200_shift_bits_dev.argtypes = [vp, u8p, C.c_uint64, C.c_int, u8p]
     L.bz2b200_merge_streams.argtypes = [C.c_int, C.c_int, vp, u64p, vp, u32p, u8p, C.c_size_t, szp]
@@ -293,6 +294,10 @@ class Engine:
         self._chk(self._L.bz2b200_compress_range(self._h, a.ctypes.data, a.size, level, starts.ctypes.data, nblocks,
                                                  first, count, out.ctypes.data, cap, C.byref(bits), crcs.ctypes.data))
         return out[:(bits.value + 7) // 8].tobytes(), int(bits.value), crcs[:count].copy()
+
+    def shard_scan(self, d_win_ptr, win_lo, win_len, n_total, level):
+        """Per-position scans of a window (needs no hand-off; a following shard_plan on the same window reuses them)."""
+        self._chk(self._L.bz2b200_shard_scan_dev(self._h, d_win_ptr, win_lo, win_len, n_total, level))
 
     def shard_plan(self, d_win_ptr, win_lo, win_len, n_total, level, start, stop_at):
         """Plans the blocks starting in [start, stop_at) -> (next_start, nblocks); raises E_CAP if the window is short."""

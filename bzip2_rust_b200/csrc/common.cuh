@@ -216,7 +216,7 @@ int bz_huf_batch(bz2b200_ctx *ctx, const Batch &B, const u16 *d_sym, const u32 *
 // rle1.cu
 int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eof, u32 off_from, u32 max_blocks,
                    Batch &B, u32 *nblocks, u32 *consumed, std::vector<u32> *h_spans, bool plan_only,
-                   u32 stop_at = 0xFFFFFFFFu, bool reuse_plan = false);
+                   u32 stop_at = 0xFFFFFFFFu, int skip = 0, u32 s0 = 0);
 int bz_crc_dev(bz2b200_ctx *ctx, const u8 *d_x, u32 n, u32 *d_crc_out);
 // api.cu
 int bz_compress_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_crc, HufOut &H);

@@ -200,6 +200,7 @@ struct ChainArgs {
     u32 is_eof;       // window ends at the end of the stream
     u32 max_blocks;
     u32 max_out;      // largest RLE1 block the batch stride can hold
+    u32 s0;           // first block start (window relative)
     u32 stop_at;      // stop the chain at the first block start >= stop_at (shard end), window relative
     u32 off_from;     // EOF bookkeeping: a group starting at/after this position since the last refill puts the
                       // reference's `remaining` counter one high (rle1.rs:207) -- see DESIGN.md "EOF corner"
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
     // all 32 lanes run the same control flow (every value is warp-uniform); lane 0 writes the results
     const bool writer = threadIdx.x == 0;
     const u32 W = a.W, B = a.B;
-    u32 s = 0, nb = 0;
+    u32 s = a.s0, nb = 0;                                       // s0: a true block start inside the scanned window
     const u32 margin = a.is_eof ? 0u : 1024u;
     while (s < W && s < a.stop_at && nb < a.max_blocks) {
         BlockRec r;
@@ -471,7 +472,10 @@ __global__ void __launch_bounds__(32) k_crc_final(const u32 *spans, u32 span_str
 // ctx->d_crc), `B` describes them, *consumed = input bytes covered.  h_rec (optional) receives the records.
 int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eof, u32 off_from, u32 max_blocks,
                    Batch &B, u32 *nblocks, u32 *consumed, std::vector<u32> *h_spans, bool plan_only, u32 stop_at,
-                   bool reuse_plan) {
+                   int skip, u32 s0) {
+    // skip bit0: the scans of the immediately preceding call on the same window are still in d_runflag;
+    // skip bit1: so is the chain result in d_misc (bz2b200_shard_scan_dev -> _plan_dev -> _compress_dev)
+    const bool skip_scan = skip & 1, skip_chain = skip & 2;
     cudaStream_t st = ctx->stream;
     u32 Bsz = (u32)level * 100000u - 19u;
     u32 max_n = Bsz + 8;                                        // RLE1 block length <= B + 5
@@ -490,7 +494,7 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
 
     // reuse_plan: the scans and the chain of the immediately preceding plan-only call on the same window are
     // still in d_runflag / d_misc (bz2b200_shard_plan_dev -> bz2b200_shard_compress_dev)
-    if (!reuse_plan && W > 0) {
+    if (!skip_scan && W > 0) {
         ctx->prof_begin(K_RS_AGG, (u64)W); k_rs_agg<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1); LAUNCH_OK();
         ctx->prof_begin(K_FLAT_SCAN, (u64)tiles * 32); k_flat_scan<<<1, 256, 0, st>>>(tagg1, tiles, nullptr); LAUNCH_OK();
         ctx->prof_begin(K_RS_APPLY, (u64)W * 5); k_rs_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1, RS, tagg2); LAUNCH_OK();
@@ -499,9 +503,10 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     }
     ChainArgs a;
     a.x = d_x; a.RS = RS; a.OUT = OUT; a.LASTQ = LASTQ; a.W = W; a.B = Bsz; a.is_eof = is_eof ? 1u : 0u;
-    a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from; a.stop_at = stop_at;
+    a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from; a.stop_at = stop_at; a.s0 = s0;
     a.rec = rec; a.nrec = d_small; a.consumed = d_small + 1;
-    if (!reuse_plan) { ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK(); }
+    if (plan_only && skip_chain) { *nblocks = 0; *consumed = 0; return BZ2B200_OK; }   // scan-only call
+    if (!skip_chain) { ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK(); }
     u32 *hs = ctx->h_small.as<u32>();
     BZ_CHECK(cudaMemcpyAsync(hs, d_small, 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));

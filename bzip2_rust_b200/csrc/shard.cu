@@ -3,10 +3,13 @@
 // The block chain s_{k+1} = e(s_k) is sequential over the whole input (rle1.rs:245-264 is an iterator),
 // but each link only needs the per-position arrays around it.  So every rank scans its own slice in
 // parallel, and the chain is handed from rank to rank as ONE number:
-//     rank r:  start_r  = (r == 0) ? 0 : recv(r-1)
-//              plan blocks whose start lies in [start_r, stop_r)        (bz2b200_shard_plan_dev)
+//     rank r:  scan own window (run starts, RLE1 output prefix)          bz2b200_shard_scan_dev   -- parallel
+//              start_r = (r == 0) ? 0 : recv(r-1)
+//              chain the blocks whose start lies in [start_r, stop_r)    bz2b200_shard_plan_dev   -- ~5 us / block
 //              send(next_start) to r+1                                    -- before the heavy work
-//              compress the planned blocks                                (bz2b200_shard_compress_dev)
+//              compress the planned blocks                                bz2b200_shard_compress_dev
+// The scan may start anywhere (it treats the window origin as a run boundary): a block that starts inside a
+// run re-chunks that run from its own start anyway, and everything behind the first run boundary is global.
 // The ranks' bit strings are then shifted to their final bit phase on the device (bz2b200_shift_bits_dev) so
 // that the ordered merge is a byte copy with an OR on the seam byte.
 #include "common.cuh"
@@ -19,14 +22,15 @@ int bz_shift_bits(bz2b200_ctx *ctx, const u8 *d_src, u64 nbits, int phase, u8 *d
 
 namespace {
 struct ShardPlan {
-    bool valid = false;
-    const u8 *d_win = nullptr;
-    u32 W = 0; int level = 0; bool eof = false; u32 off_from = 0; u32 max_blocks = 0; u32 stop_at = 0;
-    u32 nb = 0;
+    // scan state
+    bool scanned = false;
+    const u8 *d_win = nullptr; size_t win_lo = 0, win_len = 0, n_total = 0; int level = 0;
+    // chain state
+    bool planned = false;
+    bool eof = false; u32 off_from = 0, stop_rel = 0, s0 = 0, nb = 0;
 };
-// one pending plan per context (keyed by the context pointer; contexts are few)
 std::mutex g_mu;
-std::vector<std::pair<bz2b200_ctx *, ShardPlan>> g_plans;
+std::vector<std::pair<bz2b200_ctx *, ShardPlan>> g_plans;      // one pending plan per context
 ShardPlan &plan_of(bz2b200_ctx *ctx) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &p : g_plans) if (p.first == ctx) return p.second;
@@ -34,14 +38,34 @@ ShardPlan &plan_of(bz2b200_ctx *ctx) {
     return g_plans.back().second;
 }
 constexpr u32 MAX_SHARD_BLOCKS = 4096;
+
+int do_scan(bz2b200_ctx *ctx, ShardPlan &P, const u8 *d_win, size_t win_lo, size_t win_len, size_t n_total, int level) {
+    P.scanned = false; P.planned = false;
+    Batch B; u32 nb = 0, consumed = 0;
+    bool eof = win_lo + win_len == n_total;
+    int rc = bz_rle1_window(ctx, d_win, (u32)win_len, level, eof, 0, MAX_SHARD_BLOCKS, B, &nb, &consumed, nullptr, true,
+                            0xFFFFFFFFu, /*skip chain*/ 2, 0);
+    if (rc) return rc;
+    P.scanned = true; P.d_win = d_win; P.win_lo = win_lo; P.win_len = win_len; P.n_total = n_total; P.level = level;
+    return BZ2B200_OK;
+}
 }  // namespace
 
 extern "C" {
 
-// d_win[0 .. win_len) = bytes [win_lo, win_lo + win_len) of a stream of n_total bytes, on this context's GPU.
-// Plans every block whose first byte lies in [start, stop_at) (absolute offsets; `start` must be a true block
-// start inside the window).  *next_start = first block start >= stop_at (or n_total).  Returns
-// BZ2B200_E_CAP if the window ends before the last such block does (upload more and call again).
+// Phase 1 (needs no hand-off): scans d_win[0 .. win_len) = bytes [win_lo, win_lo + win_len) of the stream.
+int bz2b200_shard_scan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
+                           int level) {
+    if (!ctx || !d_win || level < 1 || level > 9 || win_lo + win_len > n_total || win_len > 0xFFFFFF00ull || win_len == 0)
+        return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    return do_scan(ctx, plan_of(ctx), d_win, win_lo, win_len, n_total, level);
+}
+
+// Phase 2: chains every block whose first byte lies in [start, stop_at) (absolute offsets; `start` must be a true
+// block start).  *next_start = first block start >= stop_at (or n_total).  Scans first unless the same window was
+// just scanned.  BZ2B200_E_CAP: the window ends before the last such block does (lengthen it and call again).
 int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
                            int level, size_t start, size_t stop_at, size_t *next_start, uint32_t *nblocks) {
     if (!ctx || !d_win || !next_start || !nblocks || level < 1 || level > 9 || win_lo + win_len > n_total ||
@@ -50,39 +74,44 @@ int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     ShardPlan &P = plan_of(ctx);
-    P.valid = false;
+    P.planned = false;
     *nblocks = 0;
     // the previous rank's last block may already cover this whole shard: nothing to do, pass the chain on
-    if (start >= stop_at || start >= n_total) { *next_start = start; P.nb = 0; P.valid = true; P.d_win = nullptr; return BZ2B200_OK; }
+    if (start >= stop_at || start >= n_total) { *next_start = start; P.nb = 0; P.planned = true; return BZ2B200_OK; }
     if (start < win_lo) return BZ2B200_E_ARG;
     if (start >= win_lo + win_len) return BZ2B200_E_CAP;          // window does not reach the first block yet
-    const u8 *x = d_win + (start - win_lo);
-    u32 W = (u32)(win_lo + win_len - start);
+    bool same = P.scanned && P.d_win == d_win && P.win_lo == win_lo && P.win_len == win_len && P.n_total == n_total &&
+                P.level == level;
+    if (!same) {
+        int rc = do_scan(ctx, P, d_win, win_lo, win_len, n_total, level);
+        if (rc) return rc;
+    }
     bool eof = win_lo + win_len == n_total;
-    u32 stop_rel = (u32)std::min<size_t>(stop_at - start, 0xFFFFFFF0u);
+    u32 W = (u32)win_len;
+    u32 s0 = (u32)(start - win_lo);
+    u32 stop_rel = (u32)std::min<size_t>(stop_at - win_lo, 0xFFFFFFF0u);
+    u32 off_from = off_from_for(n_total, level, win_lo);
     Batch B; u32 nb = 0, consumed = 0;
-    u32 off_from = off_from_for(n_total, level, start);
-    int rc = bz_rle1_window(ctx, x, W, level, eof, off_from, MAX_SHARD_BLOCKS, B, &nb, &consumed, nullptr, true, stop_rel, false);
+    int rc = bz_rle1_window(ctx, d_win, W, level, eof, off_from, MAX_SHARD_BLOCKS, B, &nb, &consumed, nullptr, true, stop_rel,
+                            /*skip scans*/ 1, s0);
     if (rc) return rc;
-    // the chain stopped early if it ran out of window before reaching stop_at
-    if (consumed < stop_rel && !(eof && consumed == W)) return BZ2B200_E_CAP;
-    *next_start = start + consumed;
+    if (consumed < stop_rel && !(eof && consumed == W)) return BZ2B200_E_CAP;   // ran out of window (or 4096 blocks)
+    *next_start = win_lo + consumed;
     *nblocks = nb;
-    P.valid = true; P.d_win = x; P.W = W; P.level = level; P.eof = eof; P.off_from = off_from;
-    P.max_blocks = MAX_SHARD_BLOCKS; P.stop_at = stop_rel; P.nb = nb;
+    P.planned = true; P.eof = eof; P.off_from = off_from; P.stop_rel = stop_rel; P.s0 = s0; P.nb = nb;
     return BZ2B200_OK;
 }
 
-// Compresses the blocks of the preceding bz2b200_shard_plan_dev call (same context, window still resident).
-// d_out receives one bit string (no stream header/footer); block_crcs[nblocks].
+// Phase 3: compresses the blocks of the preceding bz2b200_shard_plan_dev call (same context, window still
+// resident).  d_out receives one bit string (no stream header/footer); block_crcs[nblocks].
 int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
                                uint32_t *block_crcs) {
     if (!ctx || !d_out || !out_bits) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     ShardPlan &P = plan_of(ctx);
-    if (!P.valid) { ctx->err = "shard_compress: no pending plan"; return BZ2B200_E_ARG; }
-    P.valid = false;
+    if (!P.planned) { ctx->err = "shard_compress: no pending plan"; return BZ2B200_E_ARG; }
+    P.planned = false;
     *out_bits = 0;
     cudaStream_t st = ctx->stream;
     if (ctx->timing) cudaEventRecord(ctx->ev_total[0], st);
@@ -90,8 +119,9 @@ int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap,
     if (P.nb == 0) return BZ2B200_OK;
     if (!block_crcs) return BZ2B200_E_ARG;
     Batch B; u32 nb = 0, consumed = 0;
-    int rc = bz_rle1_window(ctx, P.d_win, P.W, P.level, P.eof, P.off_from, P.max_blocks, B, &nb, &consumed, nullptr, false,
-                            P.stop_at, true);
+    int rc = bz_rle1_window(ctx, P.d_win, (u32)P.win_len, P.level, P.eof, P.off_from, MAX_SHARD_BLOCKS, B, &nb, &consumed,
+                            nullptr, false, P.stop_rel, /*skip scans + chain*/ 3, P.s0);
+    P.scanned = false;
     if (rc) return rc;
     if (nb != P.nb) { ctx->err = "shard_compress: plan changed"; return BZ2B200_E_ARG; }
     // the BWT workspace is sized per batch; a shard is compressed in sub-batches of whole blocks

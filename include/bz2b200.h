@@ -93,6 +93,10 @@ int bz2b200_compress_range_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, 
  * bz2b200_shard_compress_dev then compresses exactly those blocks (window must still be resident). */
 int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
                            int level, size_t start, size_t stop_at, size_t *next_start, uint32_t *nblocks);
+/* Optional first phase of bz2b200_shard_plan_dev that needs no hand-off (run it while the chain arrives): the
+ * per-position scans of the window.  A following shard_plan on the same window skips them. */
+int bz2b200_shard_scan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
+                           int level);
 int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
                                uint32_t *block_crcs);
 /* d_dst = d_src shifted right by phase (0..7) bits, so a rank can pre-align its bit string to its final offset

@@ -28,6 +28,8 @@ def _sharded(engine, data, level, world, window_slack):
         while True:
             win_len = min(total - lo, hi - lo + slack)
             d_win = d_in[lo:lo + win_len].clone()
+            if r % 2 == 0:
+                engine.shard_scan(d_win.data_ptr(), lo, win_len, total, level)     # optional early phase
             try:
                 nxt, nb = engine.shard_plan(d_win.data_ptr(), lo, win_len, total, level, start, hi)
                 break
