@@ -242,10 +242,19 @@ def _main(args, real_stdout):
         if world == 1:
             state["dev_len"] = eng.compress_dev(d_in.data_ptr(), total, level, d_out.data_ptr(), cap)
             return
-        win_hi = min(total, my_hi + (64 << 20))                # look-ahead for the last block of the slice
+        look = 4 << 20                                         # look-ahead for the last block of the slice
+        win_hi = min(total, my_hi + look)
         eng.shard_scan(d_in.data_ptr() + my_lo, my_lo, win_hi - my_lo, total, level)     # parallel on all ranks
         start = chain_recv()
-        nxt, nb = eng.shard_plan(d_in.data_ptr() + my_lo, my_lo, win_hi - my_lo, total, level, start, my_hi)
+        while True:
+            try:
+                nxt, nb = eng.shard_plan(d_in.data_ptr() + my_lo, my_lo, win_hi - my_lo, total, level, start, my_hi)
+                break
+            except bz.Bz2B200Error as e:                       # a block spans more input than the look-ahead
+                if e.rc != bz.E_CAP or win_hi >= total:
+                    raise
+                look *= 8
+                win_hi = min(total, my_hi + look)
         chain_send(nxt)
         bits, crcs = eng.shard_compress(nb, d_out.data_ptr(), cap)
         state["dev_bits"], state["dev_crcs"] = bits, crcs
