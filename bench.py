@@ -214,7 +214,14 @@ def _main(args, real_stdout):
         d_shift = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
         win_cap = min(total - my_lo, per + (64 << 20))
         d_win = torch.empty(win_cap, dtype=torch.uint8, device=dev)
-        d_final = torch.empty(h_out.numel(), dtype=torch.uint8, device=dev) if rank == 0 else None
+        h_part = torch.empty(cap + 64, dtype=torch.uint8).pin_memory()
+        # the merged stream lives in host memory shared by the ranks (one process per GPU): every rank writes its shard
+        shm_path = "/dev/shm/bz2b200_bench_%s.out" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            with open(shm_path, "wb") as f:
+                f.truncate(h_out.numel())
+        dist.barrier()
+        shm = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(h_out.numel(),))
 
     def barrier():
         torch.cuda.synchronize()
@@ -300,42 +307,39 @@ def _main(args, real_stdout):
             pos += b_r
         phase = offs[rank] % 8
         eng.shift_bits(d_out.data_ptr(), bits, phase, d_shift.data_ptr())
-        nbytes = (bits + phase + 7) // 8
-        maxbytes = max((b_r + 7 + 7) // 8 for b_r, _ in metas) + 8
+        nby = (bits + phase + 7) // 8
+        lo = offs[rank] // 8
+        # every rank copies its own pre-shifted shard over its own PCIe link into the shared host output
+        h_part[:nby].copy_(d_shift[:nby])
+        torch.cuda.synchronize()
+        skip = 1 if (rank > 0 and phase > 0) else 0            # the seam byte is shared with the previous rank
+        shm[lo + skip:lo + nby] = h_part[skip:nby].numpy()
+        if rank == world - 1:
+            shm[lo + nby:lo + nby + 16] = 0                    # footer area (OR-ed in below)
         maxcrc = max(n_r for _, n_r in metas) + 1
-        part = d_shift[:maxbytes]
         crc_t = torch.zeros(maxcrc, dtype=torch.int64, device=dev)
         crc_t[:nb] = torch.from_numpy(crcs.astype(np.int64)).to(dev)
+        gc_ = [torch.empty(maxcrc, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(gc_, crc_t)                            # doubles as the barrier before the seam ORs
+        torch.cuda.synchronize()
+        if skip:
+            shm[lo] |= int(h_part[0])
+        total_bits = pos + 80
+        nfinal = (total_bits + 7) // 8
         if rank == 0:
-            gp = [torch.empty(maxbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
-            gc_ = [torch.empty(maxcrc, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.gather(part, gp, 0)
-            dist.gather(crc_t, gc_, 0)
-            total_bits = pos + 80
-            nfinal = (total_bits + 7) // 8
-            d_final[:nfinal + 8].zero_()
             combined = 0
             for r in range(world):
-                b_r, n_r = metas[r]
-                nby = (b_r + offs[r] % 8 + 7) // 8
-                lo = offs[r] // 8
-                d_final[lo:lo + nby].bitwise_or_(gp[r][:nby])
-                for cval in gc_[r][:n_r].tolist():
+                for cval in gc_[r][:metas[r][1]].tolist():
                     combined = (((combined << 1) | (combined >> 31)) & 0xFFFFFFFF) ^ cval      # crc.rs:25-27
-            h_out[:nfinal].copy_(d_final[:nfinal])
-            torch.cuda.synchronize()
-            buf = h_out.numpy()
-            buf[0:4] = np.frombuffer(b"BZh" + bytes([48 + level]), dtype=np.uint8)                # bitwriter.rs:67-72
+            shm[0:4] = np.frombuffer(b"BZh" + bytes([48 + level]), dtype=np.uint8)                # bitwriter.rs:67-72
             foot = ((0x177245385090 << 32) | combined) << ((8 - total_bits % 8) % 8)                # bitwriter.rs:103-114
-            fb = foot.to_bytes(11, "big")
-            tail = np.frombuffer(fb, dtype=np.uint8)
-            fstart = nfinal - 11
-            buf[fstart:nfinal] |= tail
+            state["foot"] = (nfinal, np.frombuffer(foot.to_bytes(11, "big"), dtype=np.uint8))
+        dist.barrier()                                         # all seam bytes are in place
+        if rank == 0:
+            nfinal, tail = state["foot"]
+            shm[nfinal - 11:nfinal] |= tail
             state["merged_len"] = nfinal
-            return h2d, nfinal
-        dist.gather(part, None, 0)
-        dist.gather(crc_t, None, 0)
-        return h2d, 0
+        return h2d, nby
 
     # ---- warm-up ----
     eng.set_timing(2)
@@ -395,7 +399,7 @@ def _main(args, real_stdout):
             verified = (stream == dev_stream) and (bz2.decompress(stream) == h_in.numpy().tobytes())
             clen = out_len.value
         else:
-            stream = h_out[:state["merged_len"]].numpy().tobytes()
+            stream = bytes(shm[:state["merged_len"]])
             verified = bz2.decompress(stream) == h_in.numpy().tobytes()
             # and the sharded stream is the same bytes one GPU produces for the whole input
             one = eng.compress(h_in.numpy(), level)
@@ -458,6 +462,10 @@ def _main(args, real_stdout):
     }
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
+        try:
+            os.unlink(shm_path)
+        except OSError:
+            pass
         dist.destroy_process_group()
     return 0
 
