@@ -275,13 +275,18 @@ def _main(args, real_stdout):
                 raise RuntimeError("compress_stream failed: %d %s" % (rc, L.bz2b200_last_error(eng._h)))
             return total, out_len.value
         # upload own slice (+ look-ahead for the last block, grown on demand) while the chain arrives
+        tr = [("t0", time.perf_counter())]
+        mark = lambda name: tr.append((name, time.perf_counter()))
         look = 2 << 20
         win_len = min(total - my_lo, (my_hi - my_lo) + look)
         d_win[:win_len].copy_(h_in[my_lo:my_lo + win_len], non_blocking=True)
         torch.cuda.synchronize()
         h2d = win_len
+        mark("h2d")
         eng.shard_scan(d_win.data_ptr(), my_lo, win_len, total, level)
+        mark("scan")
         start = chain_recv()
+        mark("chain_recv")
         while True:
             try:
                 nxt, nb = eng.shard_plan(d_win.data_ptr(), my_lo, win_len, total, level, start, my_hi)
@@ -295,7 +300,9 @@ def _main(args, real_stdout):
                 h2d += new_len - win_len
                 win_len = new_len
         chain_send(nxt)
+        mark("plan+send")
         bits, crcs = eng.shard_compress(nb, d_out.data_ptr(), cap)
+        mark("compress")
         # ordered merge: exchange bit lengths, shift to the final bit phase on the device, gather, OR on rank 0
         meta = torch.tensor([bits, nb], dtype=torch.int64, device=dev)
         metas = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
@@ -310,8 +317,10 @@ def _main(args, real_stdout):
         nby = (bits + phase + 7) // 8
         lo = offs[rank] // 8
         # every rank copies its own pre-shifted shard over its own PCIe link into the shared host output
+        mark("meta+shift")
         h_part[:nby].copy_(d_shift[:nby])
         torch.cuda.synchronize()
+        mark("d2h")
         skip = 1 if (rank > 0 and phase > 0) else 0            # the seam byte is shared with the previous rank
         shm[lo + skip:lo + nby] = h_part[skip:nby].numpy()
         if rank == world - 1:
@@ -320,8 +329,10 @@ def _main(args, real_stdout):
         crc_t = torch.zeros(maxcrc, dtype=torch.int64, device=dev)
         crc_t[:nb] = torch.from_numpy(crcs.astype(np.int64)).to(dev)
         gc_ = [torch.empty(maxcrc, dtype=torch.int64, device=dev) for _ in range(world)]
+        mark("shm_write")
         dist.all_gather(gc_, crc_t)                            # doubles as the barrier before the seam ORs
         torch.cuda.synchronize()
+        mark("crc_allgather")
         if skip:
             shm[lo] |= int(h_part[0])
         total_bits = pos + 80
@@ -339,6 +350,10 @@ def _main(args, real_stdout):
             nfinal, tail = state["foot"]
             shm[nfinal - 11:nfinal] |= tail
             state["merged_len"] = nfinal
+        mark("footer")
+        if os.environ.get("BENCH_TRACE"):
+            sys.stderr.write("[trace rank %d] " % rank + " ".join("%s=%.2f" % (n, (t - tr[i][1]) * 1e3)
+                                                                  for i, (n, t) in enumerate(tr[1:])) + "\n")
         return h2d, nby
 
     # ---- warm-up ----
