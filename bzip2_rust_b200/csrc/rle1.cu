@@ -289,7 +289,15 @@ __global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
             long long target = (long long)B - 1 - off;          // first x >= re with OUT[x] >= target
             u32 x1;
             if ((long long)a.OUT[W] < target) x1 = W + 1;       // never reached inside the window
-            else x1 = warp_lower_bound(a.OUT, re, W, target);
+            else {
+                // run-free data emits one byte per input byte, so the answer is usually re + (bytes still to emit):
+                // verify that guess with two independent loads before falling back to the search
+                long long need = target - (long long)a.OUT[re];
+                u64 guess = (u64)re + (u64)(need > 0 ? need : 0);
+                if (need <= 0) x1 = re;
+                else if (guess <= W && (long long)a.OUT[guess] >= target && (long long)a.OUT[guess - 1] < target) x1 = (u32)guess;
+                else x1 = warp_lower_bound(a.OUT, re, W, target);
+            }
             u32 gl = NOQ;                                       // start of the last taken global group
             if (x1 <= W) {
                 // the only group that can sit exactly at the limit starts in [x1, x1+3]
