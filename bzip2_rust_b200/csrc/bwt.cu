@@ -491,16 +491,31 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     dim3 gfull_r((B.max_n + R_TILE - 1) / R_TILE, B.nblk);
     const u32 rtiles = B.stride / R_TILE;
 
+    // one-kernel radix passes (decoupled look-back): digit totals, tile state (aliases thist), tickets
+    const u32 DSTRIDE = 8 * 256;                                 // per block: up to 8 passes x 256 digit offsets
+    BZ_CHECK(ctx->d_R.ensure(((size_t)B.nblk * DSTRIDE + 256) * 4));
+    u32 *dcounts = ctx->d_R.as<u32>();
+    u32 *tickets = dcounts + (size_t)B.nblk * DSTRIDE;          // one counter per epoch
+    u32 *tstate = W.thist;
+    BZ_CHECK(cudaMemsetAsync(dcounts, 0, ((size_t)B.nblk * DSTRIDE + 256) * 4, st));
+    BZ_CHECK(cudaMemsetAsync(tstate, 0, (size_t)B.nblk * rtiles * 256 * 4, st));
+    u32 epoch = 0;
+
     // ---- 1. initial 8-byte LSD sort (implicit keys) ----
     u32 *cur = nullptr, *src = nullptr;
     u32 *bufs[2] = {W.SA, W.SA2};
+    // every pass has the same digit totals: the block's byte histogram (each byte is digit p of exactly one rotation)
+    ctx->prof_begin(K_RADIX_HIST0, ne_act); radix::k_byte_hist<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, dcounts, B.stride, DSTRIDE); LAUNCH_OK();
+    ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * DSTRIDE * 4); radix::k_digit_scan<<<B.nblk * 8, 256, 0, st>>>(dcounts); LAUNCH_OK();
     for (int p = 0; p < 8; p++) {
-        RadixArgs a{};
+        radix::SweepArgs s{};
+        RadixArgs &a = s.r;
         a.T = B.T; a.len = B.len; a.cnt = B.len; a.sa_in = src; a.sa_out = bufs[p & 1];
         a.thist = W.thist; a.stride = B.stride; a.rtiles = rtiles; a.off = 7 - p;
-        ctx->prof_begin(K_RADIX_HIST0, ne_act * 5); radix::k_radix_hist<0><<<gfull_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
-        ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * rtiles * 2048); radix::k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, B.len, rtiles); LAUNCH_OK();
-        ctx->prof_begin(K_RADIX_SCATTER0, ne_act * 9); radix::k_radix_scatter<0><<<gfull_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+        epoch++;
+        s.dbase = dcounts; s.dbase_stride = DSTRIDE; s.tstate = tstate; s.ticket = tickets + epoch; s.epoch = epoch;
+        s.tiles_x = gfull_r.x;
+        ctx->prof_begin(K_RADIX_SCATTER0, ne_act * 9); radix::k_radix_onesweep<0><<<gfull_r.x * B.nblk, BZ_THREADS, 0, st>>>(s); LAUNCH_OK();
         src = bufs[p & 1];
     }
     cur = src;   // after 8 passes: bufs[1] = SA2
@@ -532,13 +547,24 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
         dim3 gl((maxc + BZ_TILE - 1) / BZ_TILE, B.nblk);
         dim3 gl_r((maxc + R_TILE - 1) / R_TILE, B.nblk);
         ctx->prof_begin(K_GATHER, lsum * 24); k_gather<<<gl, BZ_THREADS, 0, st>>>(cnt_cur, B.len, W.RANK, K0, V0, B.stride, h, B.nbits); LAUNCH_OK();
+        // digit totals of all passes from one read of the keys
+        BZ_CHECK(cudaMemsetAsync(dcounts, 0, (size_t)B.nblk * DSTRIDE * 4, st));
+        ctx->prof_begin(K_RADIX_HIST1, lsum * 8); radix::k_list_hist<<<gl, BZ_THREADS, 0, st>>>(K0, cnt_cur, dcounts, B.stride, passes); LAUNCH_OK();
+        ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * DSTRIDE * 4); radix::k_digit_scan<<<B.nblk * 8, 256, 0, st>>>(dcounts); LAUNCH_OK();
+        if (epoch + (u32)passes > 254) {                        // epochs are 8 bits: start over with a clean state array
+            BZ_CHECK(cudaMemsetAsync(tstate, 0, (size_t)B.nblk * rtiles * 256 * 4, st));
+            BZ_CHECK(cudaMemsetAsync(tickets, 0, 256 * 4, st));
+            epoch = 0;
+        }
         for (int p = 0; p < passes; p++) {
-            RadixArgs a{};
+            radix::SweepArgs s{};
+            RadixArgs &a = s.r;
             a.T = B.T; a.len = B.len; a.cnt = cnt_cur; a.key_in = K0; a.key_out = K1; a.val_in = V0; a.val_out = V1;
             a.thist = W.thist; a.stride = B.stride; a.rtiles = rtiles; a.shift = 8 * p;
-            ctx->prof_begin(K_RADIX_HIST1, lsum * 8); radix::k_radix_hist<1><<<gl_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
-            ctx->prof_begin(K_RADIX_SCAN, (u64)B.nblk * rtiles * 2048); radix::k_radix_scan<<<B.nblk, 256, 0, st>>>(W.thist, cnt_cur, rtiles); LAUNCH_OK();
-            ctx->prof_begin(K_RADIX_SCATTER1, lsum * 24); radix::k_radix_scatter<1><<<gl_r, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+            epoch++;
+            s.dbase = dcounts + p * 256; s.dbase_stride = DSTRIDE; s.tstate = tstate; s.ticket = tickets + epoch; s.epoch = epoch;
+            s.tiles_x = gl_r.x;
+            ctx->prof_begin(K_RADIX_SCATTER1, lsum * 24); radix::k_radix_onesweep<1><<<gl_r.x * B.nblk, BZ_THREADS, 0, st>>>(s); LAUNCH_OK();
             u64 *tk = K0; K0 = K1; K1 = tk;
             u32 *tv = V0; V0 = V1; V1 = tv;
         }
