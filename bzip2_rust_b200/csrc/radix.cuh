@@ -186,7 +186,11 @@ struct SweepArgs {
     u32 *ticket;           // one counter for this launch (zeroed before)
     u32 epoch;             // 1..255
     u32 tiles_x;           // tiles per block covered by the grid
+    u32 nblk;
 };
+constexpr u32 SWEEP_GROUP = 32;
+// grid size for a sweep launch: whole groups of SWEEP_GROUP blocks
+static inline u32 sweep_grid(u32 tiles_x, u32 nblk) { return ((nblk + SWEEP_GROUP - 1) / SWEEP_GROUP) * SWEEP_GROUP * tiles_x; }
 
 __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) {
     u32 v;
@@ -204,7 +208,13 @@ __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_onesweep(SweepArgs s) {
     if (threadIdx.x == 0) s_ticket = atomicAdd(s.ticket, 1u);
     __syncthreads();
     u32 ticket = s_ticket;
-    u32 b = ticket / s.tiles_x, t = ticket % s.tiles_x;
+    // Tickets walk the tiles of SWEEP_GROUP blocks in lock step (tile 0 of each block, then tile 1, ...): only a few
+    // tiles of any one block are in flight, so the look-back is short, while the text of only SWEEP_GROUP blocks
+    // (tens of MB, L2 resident) is being gathered from at a time.
+    u32 per_group = SWEEP_GROUP * s.tiles_x;
+    u32 g = ticket / per_group, r = ticket % per_group;
+    u32 b = g * SWEEP_GROUP + r % SWEEP_GROUP, t = r / SWEEP_GROUP;
+    if (b >= s.nblk) return;
     u32 cnt = a.cnt[b];
     u32 base = t * R_TILE;
     if (base >= cnt) return;
