@@ -514,7 +514,7 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
         a.thist = W.thist; a.stride = B.stride; a.rtiles = rtiles; a.off = 7 - p;
         epoch++;
         s.dbase = dcounts; s.dbase_stride = DSTRIDE; s.tstate = tstate; s.ticket = tickets + epoch; s.epoch = epoch;
-        s.tiles_x = gfull_r.x; s.nblk = (u32)B.nblk;
+        s.tiles_x = gfull_r.x; s.nblk = (u32)B.nblk; s.group = radix::sweep_group();
         ctx->prof_begin(K_RADIX_SCATTER0, ne_act * 9); radix::k_radix_onesweep<0><<<radix::sweep_grid(gfull_r.x, B.nblk), BZ_THREADS, 0, st>>>(s); LAUNCH_OK();
         src = bufs[p & 1];
     }
@@ -563,7 +563,7 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
             a.thist = W.thist; a.stride = B.stride; a.rtiles = rtiles; a.shift = 8 * p;
             epoch++;
             s.dbase = dcounts + p * 256; s.dbase_stride = DSTRIDE; s.tstate = tstate; s.ticket = tickets + epoch; s.epoch = epoch;
-            s.tiles_x = gl_r.x; s.nblk = (u32)B.nblk;
+            s.tiles_x = gl_r.x; s.nblk = (u32)B.nblk; s.group = radix::sweep_group();
             ctx->prof_begin(K_RADIX_SCATTER1, lsum * 24); radix::k_radix_onesweep<1><<<radix::sweep_grid(gl_r.x, B.nblk), BZ_THREADS, 0, st>>>(s); LAUNCH_OK();
             u64 *tk = K0; K0 = K1; K1 = tk;
             u32 *tv = V0; V0 = V1; V1 = tv;

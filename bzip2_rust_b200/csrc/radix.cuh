@@ -10,6 +10,7 @@
 // elements and 150 registers, i.e. one CTA per SM; ncu showed 12% warp occupancy).
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace radix {
 
@@ -187,10 +188,16 @@ struct SweepArgs {
     u32 epoch;             // 1..255
     u32 tiles_x;           // tiles per block covered by the grid
     u32 nblk;
+    u32 group;             // blocks interleaved per ticket group
 };
-constexpr u32 SWEEP_GROUP = 32;
-// grid size for a sweep launch: whole groups of SWEEP_GROUP blocks
-static inline u32 sweep_grid(u32 tiles_x, u32 nblk) { return ((nblk + SWEEP_GROUP - 1) / SWEEP_GROUP) * SWEEP_GROUP * tiles_x; }
+// blocks whose tiles are interleaved (tuning knob: env BZ2B200_SWEEP_GROUP, default 32)
+static inline u32 sweep_group() {
+    static u32 g = 0;
+    if (!g) { const char *e = getenv("BZ2B200_SWEEP_GROUP"); g = e ? (u32)atoi(e) : 32u; if (g < 1) g = 1; }
+    return g;
+}
+// grid size for a sweep launch: whole groups of blocks
+static inline u32 sweep_grid(u32 tiles_x, u32 nblk) { u32 G = sweep_group(); return ((nblk + G - 1) / G) * G * tiles_x; }
 
 __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) {
     u32 v;
@@ -211,6 +218,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_onesweep(SweepArgs s) {
     // Tickets walk the tiles of SWEEP_GROUP blocks in lock step (tile 0 of each block, then tile 1, ...): only a few
     // tiles of any one block are in flight, so the look-back is short, while the text of only SWEEP_GROUP blocks
     // (tens of MB, L2 resident) is being gathered from at a time.
+    const u32 SWEEP_GROUP = s.group;
     u32 per_group = SWEEP_GROUP * s.tiles_x;
     u32 g = ticket / per_group, r = ticket % per_group;
     u32 b = g * SWEEP_GROUP + r % SWEEP_GROUP, t = r / SWEEP_GROUP;
