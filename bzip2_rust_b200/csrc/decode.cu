@@ -305,10 +305,10 @@ static int ibwt_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_keys, u8 *d
     ctx->prof_begin(K_RADIX_SCAN, 0); radix::k_radix_scan<<<B.nblk, 256, 0, st>>>(a.thist, B.len, rtiles); LAUNCH_OK();
     ctx->prof_begin(K_RADIX_SCATTER0, B.total_n * 9); radix::k_radix_scatter<0><<<gr, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
     dim3 gs((B.max_n / SPLIT + 2 + 255) / 256, B.nblk);
-    ctx->prof_begin(K_DEC_MISC, B.total_n * 4); k_ibwt_chase<<<gs, 256, 0, st>>>(P, B.len, d_keys, B.stride, seglen, segnext, sstride); LAUNCH_OK();
-    ctx->prof_begin(K_DEC_MISC, 0); k_ibwt_rank<<<B.nblk, 32, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, vsplit, voff, vstride, nvisit); LAUNCH_OK();
+    ctx->prof_begin(K_IBWT_CHASE, B.total_n * 4); k_ibwt_chase<<<gs, 256, 0, st>>>(P, B.len, d_keys, B.stride, seglen, segnext, sstride); LAUNCH_OK();
+    ctx->prof_begin(K_IBWT_RANK, 0); k_ibwt_rank<<<B.nblk, 32, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, vsplit, voff, vstride, nvisit); LAUNCH_OK();
     dim3 gv((vstride + 255) / 256, B.nblk);
-    ctx->prof_begin(K_DEC_MISC, B.total_n * 6); k_ibwt_write<<<gv, 256, 0, st>>>(P, B.T, B.len, d_keys, B.stride, vsplit, voff, vstride, nvisit, d_out); LAUNCH_OK();
+    ctx->prof_begin(K_IBWT_WRITE, B.total_n * 6); k_ibwt_write<<<gv, 256, 0, st>>>(P, B.T, B.len, d_keys, B.stride, vsplit, voff, vstride, nvisit, d_out); LAUNCH_OK();
     return BZ2B200_OK;
 }
 
@@ -346,7 +346,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u64 *d_cand = ctx->d_dec1.as<u64>();
     u32 *d_ncand = (u32 *)(d_cand + cap);
     BZ_CHECK(cudaMemsetAsync(d_ncand, 0, 4, st));
-    ctx->prof_begin(K_DEC_MISC, n); k_dec_find_magic<<<(u32)((n + 255) / 256), 256, 0, st>>>(ctx->d_in.as<u8>(), n, d_cand, d_ncand, cap); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_MAGIC, n); k_dec_find_magic<<<(u32)((n + 255) / 256), 256, 0, st>>>(ctx->d_in.as<u8>(), n, d_cand, d_ncand, cap); LAUNCH_OK();
     u32 ncand = 0;
     BZ_CHECK(cudaMemcpyAsync(&ncand, d_ncand, 4, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
@@ -390,7 +390,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u64 *d_ooff = d_olen + nb;
     u32 *d_se = (u32 *)(d_ooff + nb);
     BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_MISC, n); k_dec_block<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_BLOCK, n); k_dec_block<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
     std::vector<DecBlock> db(nb);
     BZ_CHECK(cudaMemcpyAsync(db.data(), d_db, (size_t)nb * sizeof(DecBlock), cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
@@ -414,7 +414,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     int rc = ibwt_batch(ctx, B, d_keys, ctx->d_bwt.as<u8>());
     if (rc) return rc;
     // ---- 4. inverse RLE1 + CRC ----
-    ctx->prof_begin(K_DEC_MISC, total_n); k_dec_rle1_count<<<nb, 32, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_olen); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_RLE1_COUNT, total_n); k_dec_rle1_count<<<nb, 32, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_olen); LAUNCH_OK();
     std::vector<u64> olen(nb), ooff(nb);
     BZ_CHECK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
@@ -428,7 +428,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     BZ_CHECK(ctx->d_stream.ensure((size_t)total + 64));
     BZ_CHECK(cudaMemcpyAsync(d_ooff, ooff.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
     BZ_CHECK(cudaMemcpyAsync(d_se, se.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_MISC, total); k_dec_rle1_write<<<nb, 32, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_ooff, ctx->d_stream.as<u8>()); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_RLE1_WRITE, total); k_dec_rle1_write<<<nb, 32, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_ooff, ctx->d_stream.as<u8>()); LAUNCH_OK();
     BZ_CHECK(ctx->d_crc.ensure((size_t)nb * 4));
     rc = bz_crc_spans_dev(ctx, ctx->d_stream.as<u8>(), d_se, nb, (u32)max_span, ctx->d_crc.as<u32>());
     if (rc) return rc;

@@ -33,7 +33,7 @@ __device__ __forceinline__ int radix_digit(const RadixArgs &a, u32 b, u32 n, u32
     if (MODE == 0) {
         sa = a.sa_in ? a.sa_in[(size_t)b * a.stride + idx] : idx;
         u32 p = sa + (u32)a.off;
-        if (p >= n) p %= n;
+        if (p >= n) { p -= n; if (p >= n) p %= n; }    // off < 8: one subtraction except for blocks shorter than 8
         return a.T[(size_t)b * a.stride + p];
     } else {
         key = a.key_in[(size_t)b * a.stride + idx];
@@ -209,7 +209,8 @@ __device__ __forceinline__ void st_volatile_u32(u32 *p, u32 v) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_onesweep(SweepArgs s) {
+// 6 CTAs/SM (40 registers) for the 4-byte payload, 4 (64 registers) for the 12-byte one; 8/5 spill and are slower
+__global__ void __launch_bounds__(BZ_THREADS, MODE == 0 ? 6 : 4) k_radix_onesweep(SweepArgs s) {
     const RadixArgs &a = s.r;
     __shared__ u32 s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(s.ticket, 1u);
