@@ -271,9 +271,11 @@ __global__ void __launch_bounds__(32) k_dec_rle1_write(const u8 *blk, const u32 
     }
 }
 
+#include "decode2.cuh"   // k_dec_block2, k_rle1_inv: the versions that are launched
+
 }  // namespace
 
-#define LAUNCH_OK()                                                  \
+#define LAUNCH_OK()                                                \
     do {                                                             \
         ctx->prof_end();                                             \
         cudaError_t e_ = cudaGetLastError();                         \
@@ -390,7 +392,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u64 *d_ooff = d_olen + nb;
     u32 *d_se = (u32 *)(d_ooff + nb);
     BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_BLOCK, n); k_dec_block<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_BLOCK, n); k_dec_block2<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
     std::vector<DecBlock> db(nb);
     BZ_CHECK(cudaMemcpyAsync(db.data(), d_db, (size_t)nb * sizeof(DecBlock), cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
@@ -414,7 +416,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     int rc = ibwt_batch(ctx, B, d_keys, ctx->d_bwt.as<u8>());
     if (rc) return rc;
     // ---- 4. inverse RLE1 + CRC ----
-    ctx->prof_begin(K_DEC_RLE1_COUNT, total_n); k_dec_rle1_count<<<nb, 32, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_olen); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_RLE1_COUNT, total_n); k_rle1_inv<0><<<nb, 256, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_olen, nullptr, nullptr); LAUNCH_OK();
     std::vector<u64> olen(nb), ooff(nb);
     BZ_CHECK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
@@ -428,7 +430,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     BZ_CHECK(ctx->d_stream.ensure((size_t)total + 64));
     BZ_CHECK(cudaMemcpyAsync(d_ooff, ooff.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
     BZ_CHECK(cudaMemcpyAsync(d_se, se.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_RLE1_WRITE, total); k_dec_rle1_write<<<nb, 32, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_ooff, ctx->d_stream.as<u8>()); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_RLE1_WRITE, total); k_rle1_inv<1><<<nb, 256, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, nullptr, d_ooff, ctx->d_stream.as<u8>()); LAUNCH_OK();
     BZ_CHECK(ctx->d_crc.ensure((size_t)nb * 4));
     rc = bz_crc_spans_dev(ctx, ctx->d_stream.as<u8>(), d_se, nb, (u32)max_span, ctx->d_crc.as<u32>());
     if (rc) return rc;
