@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(32) k_dec_rle1_write(const u8 *blk, const u32 
     }
 }
 
-#include "decode2.cuh"   // k_dec_block2, k_rle1_inv: the versions that are launched
+#include "decode2.cuh"   // k_dec_block2 (superseded), k_rle1_inv
+#include "decode3.cuh"   // k_dec_block3: the entropy decoder that is launched
 
 }  // namespace
 
@@ -392,7 +393,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u64 *d_ooff = d_olen + nb;
     u32 *d_se = (u32 *)(d_ooff + nb);
     BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_BLOCK, n); k_dec_block2<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_BLOCK, n); k_dec_block3<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
     std::vector<DecBlock> db(nb);
     BZ_CHECK(cudaMemcpyAsync(db.data(), d_db, (size_t)nb * sizeof(DecBlock), cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
