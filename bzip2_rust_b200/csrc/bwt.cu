@@ -405,7 +405,8 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     u32 epoch = 0, tk = 0;
     dim3 gfull((B.max_n + BZ_TILE - 1) / BZ_TILE, B.nblk);
     // The refine kernels scatter into RANK (and SA): few blocks in flight keep that working set inside the L2.
-    static const u32 group = [] { const char *e = getenv("BZ2B200_REFINE_GROUP"); u32 g = e ? (u32)atoi(e) : 4u; return g < 1 ? 1u : g; }();
+    static const u32 group_knob = [] { const char *e = getenv("BZ2B200_REFINE_GROUP"); u32 g = e ? (u32)atoi(e) : 4u; return g < 1 ? 1u : g; }();
+    const u32 group = group_knob < (u32)B.nblk ? group_knob : (u32)B.nblk;
 
     // ---- 1. initial 8-byte LSD sort (implicit keys) ----
     // every pass has the same digit totals: the block's byte histogram (each byte is digit p of exactly one rotation)

@@ -210,14 +210,18 @@ __global__ void __launch_bounds__(BZ_THREADS, min_ctas(MODE, IPT)) k_sweep(Args 
 }
 
 // tuning knobs (environment, read once): elements per thread of the initial / list passes, interleave group
-struct Knobs { int ipt0, ipt1; u32 group; };
+struct Knobs { int ipt0, ipt1; u32 group, group_stream; };
 static inline const Knobs &knobs() {
     static Knobs k = [] {
         Knobs q;
         const char *e;
         q.ipt0 = (e = getenv("BZ2B200_SWEEP_IPT0")) ? atoi(e) : 16;
         q.ipt1 = (e = getenv("BZ2B200_SWEEP_IPT1")) ? atoi(e) : 8;
+        // gather passes: few blocks in flight keep the gathered text inside the L2; passes that only stream prefer
+        // short look-back chains (many blocks in flight).  Measured on text100m: 32 / 112.
         q.group = (e = getenv("BZ2B200_SWEEP_GROUP")) ? (u32)atoi(e) : 32u;
+        q.group_stream = (e = getenv("BZ2B200_SWEEP_GROUP_STREAM")) ? (u32)atoi(e) : 128u;
+        if (q.group_stream < 1) q.group_stream = 1;
         if (q.ipt0 != 8 && q.ipt0 != 16) q.ipt0 = 16;
         if (q.ipt1 != 8 && q.ipt1 != 16) q.ipt1 = 8;
         if (q.group < 1) q.group = 1;
@@ -235,7 +239,8 @@ static inline void launch(Args a, u32 max_cnt, cudaStream_t st) {
     u32 tile = (u32)(BZ_THREADS * ipt);
     a.tiles_x = (max_cnt + tile - 1) / tile;
     a.rtiles = a.stride / tile;
-    a.group = k.group;
+    a.group = MODE == M_GATHER ? k.group : k.group_stream;
+    if (a.group > a.nblk) a.group = a.nblk;
     u32 grid = ((a.nblk + a.group - 1) / a.group) * a.group * a.tiles_x;
     if (grid == 0) return;
     if (ipt == 8) k_sweep<MODE, 8><<<grid, BZ_THREADS, 0, st>>>(a);
