@@ -66,40 +66,177 @@ __device__ __forceinline__ void make_crc_table(u32 *tab) {
 }
 
 // ---------------------------------------------------------------------------------------
-// window scans (flat tiles over the input window; tile aggregates reuse int4 {max, max, sum})
+// window scan: RS, OUT and LASTQ in ONE pass over the input window
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BZ_THREADS) k_rs_agg(const u8 *x, u32 W, int4 *tagg) {
-    u32 base = blockIdx.x * BZ_TILE;
-    u32 i0 = base + threadIdx.x * BZ_IPT;
-    int last = -1;
+// Flat tiles of 4096 input bytes (thread = 16 consecutive bytes, loaded as aligned words).  The two running
+// quantities that cross tile borders -- the start of the current run (a max) and (last group start, emitted
+// bytes) (a max and a sum) -- come from two decoupled look-backs on 64-bit state words:
+//   [63:62] 1 = tile aggregate, 2 = inclusive prefix; [59:30] max + 1 (0 = none); [29:0] sum.
+// The first version used five kernels (aggregate / scan / apply twice) with byte loads at a 16-byte thread
+// stride; it ran at a fifth of the copy bandwidth.
+struct Pair { int a; u32 c; };
+__device__ __forceinline__ u64 pair_pack(u32 flag, Pair v) { return ((u64)flag << 62) | ((u64)(u32)(v.a + 1) << 30) | (u64)v.c; }
+__device__ __forceinline__ Pair pair_unpack(u64 w) {
+    Pair v;
+    v.a = (int)((w >> 30) & 0x3fffffffu) - 1; v.c = (u32)(w & 0x3fffffffu);
+    return v;
+}
+__device__ __forceinline__ u64 ld_vol64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_vol64(u64 *p, u64 v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+// All lanes of warp 0 call.  Lane l inspects tile hi - l: a window of 32 predecessors per L2 round trip.
+__device__ __forceinline__ Pair pair_lookback(u64 *st, u32 t, Pair agg) {
+    const int lane = threadIdx.x & 31;
+    Pair ex; ex.a = -1; ex.c = 0;
+    if (t == 0) { if (lane == 0) st_vol64(st, pair_pack(2, agg)); return ex; }
+    if (lane == 0) st_vol64(st + t, pair_pack(1, agg));
+    for (int hi = (int)t - 1;;) {
+        int tt = hi - lane;
+        u64 w = tt >= 0 ? ld_vol64(st + tt) : (2ull << 62);
+        u32 f = (u32)(w >> 62);
+        u32 incm = __ballot_sync(0xffffffffu, f == 2);
+        u32 nrm = __ballot_sync(0xffffffffu, f == 0);
+        u32 need = incm ? ((2u << (__ffs(incm) - 1)) - 1u) : 0xffffffffu;
+        if (nrm & need) continue;
+        Pair v = pair_unpack(w);
+        if (!((need >> lane) & 1u)) { v.a = -1; v.c = 0; }
 #pragma unroll
-    for (int r = 0; r < BZ_IPT; r++) {
-        u32 i = i0 + r;
-        if (i < W && (i == 0 || x[i] != x[i - 1])) last = (int)i;
+        for (int o = 16; o; o >>= 1) {
+            v.a = max(v.a, __shfl_xor_sync(0xffffffffu, v.a, o));
+            v.c += __shfl_xor_sync(0xffffffffu, v.c, o);
+        }
+        ex.a = max(ex.a, v.a); ex.c += v.c;
+        if (incm) break;
+        hi -= 32;
     }
-    __shared__ int wsi[8];
-    int tot;
-    block_excl_max(last, wsi, tot);
-    if (threadIdx.x == 0) tagg[blockIdx.x] = make_int4(tot, -1, 0, 0);
+    Pair inc; inc.a = max(ex.a, agg.a); inc.c = ex.c + agg.c;
+    if (lane == 0) st_vol64(st + t, pair_pack(2, inc));
+    return ex;
 }
 
-// exclusive scan of tile aggregates for a flat array of `tiles` tiles (single CTA)
-__global__ void __launch_bounds__(256) k_flat_scan(int4 *tagg, u32 tiles, u32 *total_out) {
+struct ScanArgs {
+    const u8 *x; u32 W;
+    u32 *RS, *OUT, *LASTQ;      // 16-byte aligned, W + 1 entries each
+    u64 *st1, *st2;             // look-back state, one word per tile, zeroed
+    u32 *ticket;                // zeroed
+};
+
+constexpr int SC_IPT = 16;
+constexpr int SC_TILE = BZ_THREADS * SC_IPT;
+
+__global__ void __launch_bounds__(BZ_THREADS) k_rle_scan(ScanArgs a) {
+    __shared__ u32 s_tile;
     __shared__ int wsi[8];
     __shared__ u32 wsu[8];
-    int ca = -1, cb = -1; u32 cc = 0;
-    for (u32 t0 = 0; t0 < tiles; t0 += 256) {
-        u32 t = t0 + threadIdx.x;
-        int4 v = (t < tiles) ? tagg[t] : make_int4(-1, -1, 0, 0);
-        int ta, tb; u32 tc;
-        int ea = block_excl_max(v.x, wsi, ta);
-        int eb = block_excl_max(v.y, wsi, tb);
-        u32 ec = block_excl_sum((u32)v.z, wsu, tc);
-        if (t < tiles) tagg[t] = make_int4(max(ea, ca), max(eb, cb), (int)(ec + cc), 0);
-        ca = max(ca, ta); cb = max(cb, tb); cc += tc;
-        __syncthreads();
+    __shared__ Pair s_ex1, s_ex2;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const u32 t = s_tile, W = a.W;
+    const u32 i0 = t * SC_TILE + tid * SC_IPT;
+    // bytes i0-4 .. i0+19 as six words v[0..5] (v[k] = bytes i0-4+4k ..), from aligned loads
+    u32 v[6];
+    {
+        uintptr_t addr = (uintptr_t)(a.x + i0) - 4;
+        const u32 *gw = (const u32 *)(addr & ~(uintptr_t)3);
+        const u32 mis = (u32)(addr & 3);
+        long long j = (long long)i0 - 4 - (long long)mis;       // index (relative to x) of the first byte of gw[0]
+        u32 w[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            long long jk = j + 4 * k;
+            w[k] = (jk + 3 >= 0 && jk < (long long)W) ? __ldg(gw + k) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[k] = __funnelshift_r(w[k], w[k + 1], mis * 8);
     }
-    if (threadIdx.x == 0 && total_out) *total_out = cc;
+#define XB(r) ((v[((r) + 4) >> 2] >> ((((r) + 4) & 3) * 8)) & 255u)      /* byte i0 + r, r in [-4, 19] */
+    // ---- run starts ----
+    int last = -1; u32 bdmask = 0;
+#pragma unroll
+    for (int r = 0; r < SC_IPT; r++) {
+        u32 i = i0 + r;
+        if (i < W && (i == 0 || XB(r) != XB(r - 1))) { last = (int)i; bdmask |= 1u << r; }
+    }
+    int tot1;
+    int rs = block_excl_max(last, wsi, tot1);
+    if (tid < 32) {
+        Pair agg; agg.a = tot1; agg.c = 0;
+        Pair ex = pair_lookback(a.st1, t, agg);
+        if (tid == 0) s_ex1 = ex;
+    }
+    __syncthreads();
+    rs = max(rs, s_ex1.a);
+    // ---- greedy parse: bytes emitted "at" each position (literal 1, group start 5, rest of a group 0) ----
+    u32 qmask = 0, litmask = 0, sum = 0;
+    int lq = -1;
+    const bool full = i0 + SC_IPT <= W;
+    u32 rsv[SC_IPT];
+#pragma unroll
+    for (int r = 0; r < SC_IPT; r++) {
+        u32 i = i0 + r;
+        rsv[r] = 0;
+        if (i < W) {
+            if ((bdmask >> r) & 1u) rs = (int)i;
+            rsv[r] = (u32)rs;
+            u32 d = i - (u32)rs;
+            u32 co = d - (d / 255u) * 255u;                     // offset inside the 255-byte chunk of the run
+            bool grp;
+            if (co >= 3) grp = true;                            // chunk start .. i are equal and i >= chunk start + 3
+            else {
+                u32 c = XB(r);
+                grp = (i - co) + 3 < W;
+                if (co < 3) grp = grp && XB(r + 1) == c;
+                if (co < 2) grp = grp && XB(r + 2) == c;
+                if (co < 1) grp = grp && XB(r + 3) == c;
+            }
+            if (!grp) { litmask |= 1u << r; sum += 1; }
+            else if (co == 0) { qmask |= 1u << r; sum += 5; lq = (int)i; }
+        }
+    }
+    if (full) {
+        uint4 *o = (uint4 *)(a.RS + i0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = make_uint4(rsv[4 * k], rsv[4 * k + 1], rsv[4 * k + 2], rsv[4 * k + 3]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < SC_IPT; r++) if (i0 + r < W) a.RS[i0 + r] = rsv[r];
+    }
+    int tq; u32 ts;
+    int q = block_excl_max(lq, wsi, tq);
+    u32 o = block_excl_sum(sum, wsu, ts);
+    if (tid < 32) {
+        Pair agg; agg.a = tq; agg.c = ts;
+        Pair ex = pair_lookback(a.st2, t, agg);
+        if (tid == 0) s_ex2 = ex;
+    }
+    __syncthreads();
+    q = max(q, s_ex2.a);
+    o += s_ex2.c;
+    u32 ov[SC_IPT], qv[SC_IPT];
+#pragma unroll
+    for (int r = 0; r < SC_IPT; r++) {
+        if ((qmask >> r) & 1u) q = (int)(i0 + r);
+        ov[r] = o; qv[r] = q < 0 ? NOQ : (u32)q;
+        o += ((litmask >> r) & 1u) + 5u * ((qmask >> r) & 1u);
+        if (i0 + r == W - 1) a.OUT[W] = o;
+    }
+    if (full) {
+        uint4 *po = (uint4 *)(a.OUT + i0), *pq = (uint4 *)(a.LASTQ + i0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            po[k] = make_uint4(ov[4 * k], ov[4 * k + 1], ov[4 * k + 2], ov[4 * k + 3]);
+            pq[k] = make_uint4(qv[4 * k], qv[4 * k + 1], qv[4 * k + 2], qv[4 * k + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < SC_IPT; r++) if (i0 + r < W) { a.OUT[i0 + r] = ov[r]; a.LASTQ[i0 + r] = qv[r]; }
+    }
+#undef XB
 }
 
 __device__ __forceinline__ bool group_start_at(const u8 *x, u32 W, u32 i, u32 rs) {
@@ -107,87 +244,6 @@ __device__ __forceinline__ bool group_start_at(const u8 *x, u32 W, u32 i, u32 rs
     if (i + 3 >= W) return false;
     u8 c = x[i];
     return x[i + 1] == c && x[i + 2] == c && x[i + 3] == c;
-}
-// bytes emitted "at" position i by the greedy parse (groups = 255-chunks of a run, >= 4 long)
-__device__ __forceinline__ u32 contrib_at(const u8 *x, u32 W, u32 i, u32 rs, bool &is_q) {
-    u32 cs = rs + ((i - rs) / 255u) * 255u;
-    bool grp = group_start_at(x, W, cs, rs);
-    is_q = grp && i == cs;
-    if (!grp) return 1;
-    return is_q ? 5u : 0u;
-}
-
-// writes RS and the aggregates for the second scan: y = last group start, z = emitted bytes
-__global__ void __launch_bounds__(BZ_THREADS) k_rs_apply(const u8 *x, u32 W, const int4 *tagg1, u32 *RS,
-                                                         int4 *tagg2) {
-    u32 base = blockIdx.x * BZ_TILE;
-    u32 i0 = base + threadIdx.x * BZ_IPT;
-    int last = -1;
-    bool bd[BZ_IPT];
-#pragma unroll
-    for (int r = 0; r < BZ_IPT; r++) {
-        u32 i = i0 + r;
-        bd[r] = i < W && (i == 0 || x[i] != x[i - 1]);
-        if (bd[r]) last = (int)i;
-    }
-    __shared__ int wsi[8];
-    __shared__ u32 wsu[8];
-    int tot;
-    int rs = max(block_excl_max(last, wsi, tot), tagg1[blockIdx.x].x);
-    int lq = -1; u32 sum = 0;
-#pragma unroll
-    for (int r = 0; r < BZ_IPT; r++) {
-        u32 i = i0 + r;
-        if (i < W) {
-            if (bd[r]) rs = (int)i;
-            RS[i] = (u32)rs;
-            bool isq;
-            sum += contrib_at(x, W, i, (u32)rs, isq);
-            if (isq) lq = (int)i;
-        }
-    }
-    int tq; u32 ts;
-    block_excl_max(lq, wsi, tq);
-    block_excl_sum(sum, wsu, ts);
-    if (threadIdx.x == 0) tagg2[blockIdx.x] = make_int4(-1, tq, (int)ts, 0);
-}
-
-// OUT[i] = exclusive prefix of emitted bytes (OUT[W] = total), LASTQ[i] = last group start <= i
-__global__ void __launch_bounds__(BZ_THREADS) k_out_apply(const u8 *x, u32 W, const int4 *tagg2, const u32 *RS,
-                                                          u32 *OUT, u32 *LASTQ) {
-    u32 base = blockIdx.x * BZ_TILE;
-    u32 i0 = base + threadIdx.x * BZ_IPT;
-    u32 cb[BZ_IPT]; bool qv[BZ_IPT];
-    int lq = -1; u32 sum = 0;
-#pragma unroll
-    for (int r = 0; r < BZ_IPT; r++) {
-        u32 i = i0 + r;
-        cb[r] = 0; qv[r] = false;
-        if (i < W) {
-            bool isq;
-            cb[r] = contrib_at(x, W, i, RS[i], isq);
-            qv[r] = isq;
-            sum += cb[r];
-            if (isq) lq = (int)i;
-        }
-    }
-    __shared__ int wsi[8];
-    __shared__ u32 wsu[8];
-    int tq; u32 ts;
-    int4 carry = tagg2[blockIdx.x];
-    int q = max(block_excl_max(lq, wsi, tq), carry.y);
-    u32 o = block_excl_sum(sum, wsu, ts) + (u32)carry.z;
-#pragma unroll
-    for (int r = 0; r < BZ_IPT; r++) {
-        u32 i = i0 + r;
-        if (i < W) {
-            if (qv[r]) q = (int)i;
-            OUT[i] = o;
-            LASTQ[i] = q < 0 ? NOQ : (u32)q;
-            o += cb[r];
-            if (i == W - 1) OUT[W] = o;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -433,7 +489,20 @@ __global__ void __launch_bounds__(256) k_crc_pieces(const u8 *x, const u32 *span
         u32 lo = (hi - s >= (u32)PIECE) ? hi - PIECE : s;
         const u8 *d = x + lo;
         u32 n = hi - lo;
-        for (u32 i = 0; i < n; i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ d[i]];
+        // Pieces of neighbouring threads are 1 KB apart, so every load instruction touches 32 cache lines: byte
+        // loads made the L1 tag stage the limiter.  Load 16 bytes at a time from 16-byte aligned addresses.
+        u32 i = 0;
+        for (; i < n && (((uintptr_t)(d + i)) & 15u); i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ d[i]];
+        for (; i + 16 <= n; i += 16) {
+            uint4 q = *(const uint4 *)(d + i);
+            u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) crc = (crc << 8) ^ tab[(crc >> 24) ^ ((w[k] >> (8 * j)) & 255u)];
+            }
+        }
+        for (; i < n; i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ d[i]];
     }
     // CTA partial = sum_j crc_j * X^j  (j = threadIdx.x): pairwise tree with powers X^(2^l)
     red[threadIdx.x] = crc;
@@ -489,25 +558,26 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     u32 max_n = Bsz + 8;                                        // RLE1 block length <= B + 5
     u32 stride = ((max_n + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE;
     u32 tiles = (W + BZ_TILE - 1) / BZ_TILE;
-    BZ_CHECK(ctx->d_runflag.ensure(((size_t)W + 1) * 4 * 3 + 64));
+    const size_t W4 = ((size_t)W + 1 + 3) & ~(size_t)3;          // entries per array, keeps all three 16-byte aligned
+    BZ_CHECK(ctx->d_runflag.ensure(W4 * 4 * 3 + 64));
     u32 *RS = ctx->d_runflag.as<u32>();
-    u32 *OUT = RS + ((size_t)W + 1);
-    u32 *LASTQ = OUT + ((size_t)W + 1);
-    BZ_CHECK(ctx->d_misc.ensure((size_t)tiles * sizeof(int4) * 2 + (size_t)max_blocks * sizeof(BlockRec) + 256));
-    int4 *tagg1 = ctx->d_misc.as<int4>();
-    int4 *tagg2 = tagg1 + tiles;
-    BlockRec *rec = (BlockRec *)(tagg2 + tiles);
+    u32 *OUT = RS + W4;
+    u32 *LASTQ = OUT + W4;
+    const size_t state_bytes = ((size_t)tiles * 8 * 2 + 64 + 15) & ~(size_t)15;     // st1 | st2 | ticket
+    BZ_CHECK(ctx->d_misc.ensure(state_bytes + (size_t)max_blocks * sizeof(BlockRec) + 256));
+    u64 *st1 = ctx->d_misc.as<u64>();
+    u64 *st2 = st1 + tiles;
+    u32 *ticket = (u32 *)(st2 + tiles);
+    BlockRec *rec = (BlockRec *)(ctx->d_misc.as<u8>() + state_bytes);
     u32 *d_small = (u32 *)(rec + max_blocks);                   // [0]=nrec [1]=consumed
     BZ_CHECK(ctx->h_small.ensure(64 + (size_t)max_blocks * sizeof(BlockRec)));
 
-    // reuse_plan: the scans and the chain of the immediately preceding plan-only call on the same window are
-    // still in d_runflag / d_misc (bz2b200_shard_plan_dev -> bz2b200_shard_compress_dev)
+    // skip_scan: the scan of the immediately preceding call on the same window is still in d_runflag
     if (!skip_scan && W > 0) {
-        ctx->prof_begin(K_RS_AGG, (u64)W); k_rs_agg<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1); LAUNCH_OK();
-        ctx->prof_begin(K_FLAT_SCAN, (u64)tiles * 32); k_flat_scan<<<1, 256, 0, st>>>(tagg1, tiles, nullptr); LAUNCH_OK();
-        ctx->prof_begin(K_RS_APPLY, (u64)W * 5); k_rs_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg1, RS, tagg2); LAUNCH_OK();
-        ctx->prof_begin(K_FLAT_SCAN, (u64)tiles * 32); k_flat_scan<<<1, 256, 0, st>>>(tagg2, tiles, nullptr); LAUNCH_OK();
-        ctx->prof_begin(K_OUT_APPLY, (u64)W * 13); k_out_apply<<<tiles, BZ_THREADS, 0, st>>>(d_x, W, tagg2, RS, OUT, LASTQ); LAUNCH_OK();
+        BZ_CHECK(cudaMemsetAsync(st1, 0, state_bytes, st));
+        ScanArgs sa;
+        sa.x = d_x; sa.W = W; sa.RS = RS; sa.OUT = OUT; sa.LASTQ = LASTQ; sa.st1 = st1; sa.st2 = st2; sa.ticket = ticket;
+        ctx->prof_begin(K_RLE_SCAN, (u64)W * 13); k_rle_scan<<<tiles, BZ_THREADS, 0, st>>>(sa); LAUNCH_OK();
     }
     ChainArgs a;
     a.x = d_x; a.RS = RS; a.OUT = OUT; a.LASTQ = LASTQ; a.W = W; a.B = Bsz; a.is_eof = is_eof ? 1u : 0u;

@@ -1,11 +1,10 @@
-rm -f gpurun_out/kt4.jsonl
-for g in 4 8 16 32 64 112; do
-  BZ2B200_SWEEP_GROUP=$g python tools/kernel_times.py 100 text 9 >> gpurun_out/kt4.jsonl 2>gpurun_out/kt4.err
-done
+python -m pytest tests/test_stream_gpu.py tests/test_shard_gpu.py tests/test_golden.py -x -q 2>&1 | tail -3
+python tools/kernel_times.py 100 text 9 1 > gpurun_out/kt5.json 2>gpurun_out/kt5.err
+python tools/kernel_times.py 256 rep 9 1 > gpurun_out/kt5r.json 2>gpurun_out/kt5r.err
 python - <<'PY'
 import sys,json
-for l in open('gpurun_out/kt4.jsonl'):
-    r=json.loads(l)
-    print(r['env'], r['adler'], r['stage_ms']['bwt'], [k for k in r['kernels'] if k[0].startswith('k_sweep')])
+for f in ('gpurun_out/kt5.json','gpurun_out/kt5r.json'):
+    r=json.loads(open(f).read())
+    print(r['corpus'], r['adler'], r['stage_ms'], r.get('libbz2_roundtrip'), r['bwt_stats'])
+    print('   ', r['kernels'][:24])
 PY
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench4.json 2> gpurun_out/bench4.err; cat gpurun_out/bench4.json | cut -c1-1200
