@@ -31,7 +31,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + sources()
+    extra = os.environ.get("BZ2B200_NVCC_EXTRA", "").split()       # experiments only, e.g. -DBZ_MTF_CH=2048
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO] + sources()
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

@@ -237,11 +237,11 @@ int bz_compress_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_crc, HufOut
     BZ_CHECK(ctx->d_used.ensure((size_t)B.nblk * 32));
     cudaStream_t st = ctx->stream;
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
-    int rc = bz_bwt_batch(ctx, B, ctx->d_bwt.as<u8>(), ctx->d_key.as<u32>());
+    int rc = bz_bwt_batch(ctx, B, ctx->d_bwt.as<u8>(), ctx->d_key.as<u32>(), ctx->d_used.as<u32>());
     if (rc) return rc;
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     rc = bz_mtf_batch(ctx, B, ctx->d_bwt.as<u8>(), ctx->d_sym.as<u16>(), ctx->d_m.as<u32>(), ctx->d_freq.as<u32>(),
-                      ctx->d_used.as<u8>());
+                      ctx->d_used.as<u8>(), true);
     if (rc) return rc;
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     rc = bz_huf_batch(ctx, B, ctx->d_sym.as<u16>(), ctx->d_m.as<u32>(), ctx->d_freq.as<u32>(), ctx->d_used.as<u8>(), 1,

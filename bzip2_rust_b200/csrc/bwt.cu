@@ -344,6 +344,14 @@ __global__ void __launch_bounds__(BZ_THREADS) k_list_refine(RefineArgs a) {
     }
 }
 
+// used-byte bitmap of every block from its byte histogram (rle2_mtf.rs:26-39 builds the same set by scanning)
+__global__ void __launch_bounds__(256) k_used_from_hist(const u32 *counts, u32 cstride, u32 *usedbits) {
+    u32 b = blockIdx.x;
+    bool used = counts[(size_t)b * cstride + threadIdx.x] != 0;
+    u32 m = __ballot_sync(0xffffffffu, used);
+    if ((threadIdx.x & 31) == 0) usedbits[b * 8 + (threadIdx.x >> 5)] = m;
+}
+
 // --------------------------------------------------------------------------------------
 // step 4
 // --------------------------------------------------------------------------------------
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(BZ_THREADS) k_bwt_out(const u8 *T, const u32 *
         if (e_ != cudaSuccess) { ctx->fail("kernel launch", e_, __FILE__, __LINE__); return BZ2B200_E_CUDA; } \
     } while (0)
 
-int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
+int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key, u32 *d_usedbits) {
     if (B.nblk == 0) return BZ2B200_OK;
     if (B.max_n > BZ2B200_MAX_BLOCK || ((uintptr_t)B.T & 7u) || (B.stride & 7u)) { ctx->err = "bwt: bad batch geometry"; return BZ2B200_E_ARG; }
     cudaStream_t st = ctx->stream;
@@ -411,6 +419,7 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key) {
     // ---- 1. initial 8-byte LSD sort (implicit keys) ----
     // every pass has the same digit totals: the block's byte histogram (each byte is digit p of exactly one rotation)
     ctx->prof_begin(K_BYTE_HIST, ne_act); sweep::k_byte_hist<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, dcounts, B.stride, DSTRIDE); LAUNCH_OK();
+    if (d_usedbits) { ctx->prof_begin(K_USED, (u64)B.nblk * 1024); k_used_from_hist<<<B.nblk, 256, 0, st>>>(dcounts, DSTRIDE, d_usedbits); LAUNCH_OK(); }
     ctx->prof_begin(K_DIGIT_SCAN, (u64)B.nblk * DSTRIDE * 4); sweep::k_digit_scan<<<B.nblk * 8, 256, 0, st>>>(dcounts); LAUNCH_OK();
     u32 *bufs[2] = {SAa, SAb};
     const u32 *src = nullptr;

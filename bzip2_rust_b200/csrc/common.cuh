@@ -197,9 +197,11 @@ __device__ __forceinline__ int block_excl_max(int v, int *ws, int &total) {
 // stage entry points (host side, implemented in the .cu files)
 int bz_stage_blocks(bz2b200_ctx *ctx, int nblk, const u8 *const *blk, const u32 *len, Batch &B);
 int bz_make_batch_dev(bz2b200_ctx *ctx, int nblk, u32 stride, u32 max_n, const u8 *dT, const u32 *dlen, Batch &B);
-int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt /*[nblk*stride]*/, u32 *d_key /*[nblk]*/);
+// d_usedbits (optional, [nblk*8] u32): the 256-bit used-byte bitmap of every block, a by-product of the byte histogram
+int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt /*[nblk*stride]*/, u32 *d_key /*[nblk]*/,
+                 u32 *d_usedbits = nullptr);
 int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym /*[nblk*(stride)]*/, u32 *d_m,
-                 u32 *d_freq /*[nblk*256]*/, u8 *d_used /*[nblk*256]*/);
+                 u32 *d_freq /*[nblk*256]*/, u8 *d_used /*[nblk*32]*/, bool used_ready = false);
 struct HufOut {
     u8 *d_out;          // [nblk * out_stride] packed bits, zero padded
     u64 *d_bits;        // [nblk]

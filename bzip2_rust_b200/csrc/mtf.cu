@@ -19,10 +19,14 @@
 //                 with the list held as 8 bytes per lane, and writes final u16 symbols straight
 //                 at their output offsets.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int CH = 1024;              // bytes per MTF chunk (one warp)
+#ifndef BZ_MTF_CH
+#define BZ_MTF_CH 2048
+#endif
+constexpr int CH = BZ_MTF_CH;         // bytes per MTF chunk (one warp)
 constexpr int WPB = BZ_THREADS / 32;  // warps (= chunks) per CTA
 
 struct ChunkAgg {
@@ -170,124 +174,8 @@ __global__ void __launch_bounds__(256) k_mtf_scan(const u32 *len, const u32 *use
     }
 }
 
-// one warp per chunk
-__global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u32 *len, const u32 *usedbits,
-                                                         const int *pm, const u32 *zbefore, const u32 *ooff,
-                                                         const u32 *m_in, u16 *sym, u32 *freq, u32 stride,
-                                                         u32 nch_stride) {
-    u32 b = blockIdx.y, n = len[b];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    u32 c = blockIdx.x * WPB + w;
-    u32 a = c * CH;
-    __shared__ int sval[WPB][256];
-    __shared__ __align__(8) u8 slist[WPB][256];
-    __shared__ u32 sfreq[256];
-    __shared__ u8 sused[256];
-    __shared__ int s_nused;
-    sfreq[threadIdx.x] = 0;
-    {   // compact list of the block's used byte values (ascending)
-        const u32 *ub = usedbits + b * 8;
-        u32 t = threadIdx.x;
-        u32 before = 0;
-        for (u32 k = 0; k < (t >> 5); k++) before += __popc(ub[k]);
-        before += __popc(ub[t >> 5] & ((1u << (t & 31)) - 1));
-        if ((ub[t >> 5] >> (t & 31)) & 1) sused[before] = (u8)t;
-        if (t == 255) s_nused = (int)(before + ((ub[7] >> 31) & 1));
-    }
-    __syncthreads();
-    const int nused = s_nused;
-    bool active = a < n;
-    u32 runa = 0, runb = 0;
-    if (active) {
-        u32 e = min(a + CH, n);
-        const u8 *L = Lall + (size_t)b * stride;
-        u16 *so = sym + (size_t)b * stride;
-        const int *v = pm + ((size_t)b * nch_stride + c) * 256;
-        for (int k = lane; k < 256; k += 32) sval[w][k] = v[k];
-        __syncwarp();
-        // start list: USED byte values sorted by last occurrence, most recent first (unused values never
-        // appear in the block, so list positions >= nused are never touched)
-        for (int j = lane; j < nused; j += 32) {
-            int s = sused[j];
-            int mine = sval[w][s], rk = 0;
-            for (int t = 0; t < nused; t++) rk += (sval[w][sused[t]] > mine);
-            slist[w][rk] = (u8)s;
-        }
-        __syncwarp();
-        u64 lst = ((const u64 *)slist[w])[lane];   // list positions 8*lane .. 8*lane+7, position p in byte p&7
-        u32 front = slist[w][0];
-        u32 z = zbefore[(size_t)b * nch_stride + c];
-        u32 o = ooff[(size_t)b * nch_stride + c];
-        const u32 o_start = o;
-        u32 obase = o & ~31u;
-        u32 staged = 0;
-#define EMIT(SYMV)                                                                    \
-        do {                                                                          \
-            if ((o & 31u) == (u32)lane) staged = (SYMV);                              \
-            o++;                                                                      \
-            if ((o & 31u) == 0) {                                                     \
-                if (obase + lane >= o_start) so[obase + lane] = (u16)staged;          \
-                obase = o;                                                            \
-            }                                                                         \
-        } while (0)
-#define FLUSH_ZEROS()                                                                 \
-        do {                                                                          \
-            u32 zz = z + 1; int nd = 31 - __clz(zz);                                  \
-            for (int q = 0; q < nd; q++) { u32 bit = (zz >> q) & 1u; if (bit) runb++; else runa++; EMIT(bit); } \
-            z = 0;                                                                    \
-        } while (0)
-        for (u32 i0 = a; i0 < e; i0 += 32) {
-            u32 my = (i0 + lane < e) ? L[i0 + lane] : 0;
-            int cntk = (int)min(32u, e - i0);
-            for (int k = 0; k < cntk; k++) {
-                u32 ch = __shfl_sync(0xffffffffu, my, k);
-                if (ch == front) { z++; continue; }
-                if (z) FLUSH_ZEROS();
-                // locate ch in the list
-                u64 x = lst ^ (0x0101010101010101ull * ch);
-                u64 zm = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
-                unsigned bal = __ballot_sync(0xffffffffu, zm != 0);
-                int Lh = __ffs(bal) - 1;
-                int kb = (__ffsll((long long)zm) - 1) >> 3;      // byte index inside the holder lane
-                kb = __shfl_sync(0xffffffffu, kb, Lh);
-                u32 pos = (u32)Lh * 8 + (u32)kb;
-                // shift [0,pos) up by one, put ch at the front
-                u32 topbyte = (u32)(lst >> 56);
-                u32 incoming = __shfl_up_sync(0xffffffffu, topbyte, 1);
-                if (lane == 0) incoming = ch;
-                if (lane < Lh) lst = (lst << 8) | incoming;
-                else if (lane == Lh) {
-                    u64 lowmask = kb ? ((1ull << (8 * kb)) - 1) : 0ull;           // bytes below kb
-                    u64 keepmask = (kb == 7) ? 0ull : ~((1ull << (8 * (kb + 1))) - 1);   // bytes above kb
-                    lst = (lst & keepmask) | (((lst & lowmask) << 8) | incoming);
-                }
-                front = ch;
-                if (lane == 0) atomicAdd(&sfreq[pos], 1u);
-                EMIT(pos + 1);
-            }
-        }
-        bool next_nz = (e >= n) ? true : (L[e] != L[e - 1]);
-        if (z && next_nz) FLUSH_ZEROS();
-        if (e >= n) { EMIT(m_in[b] >= 1 ? 0 : 0); o--; }   // placeholder slot for EOB, rewritten below
-        // final partial flush
-        if (obase + lane >= o_start && obase + lane < o) so[obase + lane] = (u16)staged;
-        if (e >= n && lane == 0) {
-            u32 nused = 0;
-            for (int k = 0; k < 8; k++) nused += __popc(usedbits[b * 8 + k]);
-            so[m_in[b] - 1] = (u16)(nused + 1);
-        }
-#undef EMIT
-#undef FLUSH_ZEROS
-    }
-    if (lane == 0 && active) {
-        if (runa) atomicAdd(&sfreq[0], runa);
-        if (runb) atomicAdd(&sfreq[1], runb);
-    }
-    __syncthreads();
-    if (sfreq[threadIdx.x]) atomicAdd(&freq[b * 256 + threadIdx.x], sfreq[threadIdx.x]);
-}
-
-#include "mtf_emit.cuh"   // k_mtf_emit2: the version that is launched
+#include "mtf_emit.cuh"    // k_mtf_emit2: byte-serial replay (kept for A/B: BZ2B200_MTF_V2=1)
+#include "mtf_emit3.cuh"   // k_mtf_emit3: position-parallel replay, the version that is launched
 
 }  // namespace
 
@@ -300,7 +188,7 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit(const u8 *Lall, const u
 
 // d_used receives the 256-bit used bitmap per block as 8 u32 words ([nblk*8] u32 = 32 bytes/block).
 int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, u32 *d_m, u32 *d_freq,
-                 u8 *d_used) {
+                 u8 *d_used, bool used_ready) {
     if (B.nblk == 0) return BZ2B200_OK;
     cudaStream_t st = ctx->stream;
     const u64 ne_act = B.total_n;
@@ -314,16 +202,18 @@ int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, 
     u32 *zbefore = (u32 *)(agg + nchunks);
     u32 *ooff = zbefore + nchunks;
     u32 *usedbits = (u32 *)d_used;
-    BZ_CHECK(cudaMemsetAsync(usedbits, 0, (size_t)B.nblk * 32, st));
+    if (!used_ready) BZ_CHECK(cudaMemsetAsync(usedbits, 0, (size_t)B.nblk * 32, st));
     BZ_CHECK(cudaMemsetAsync(d_freq, 0, (size_t)B.nblk * 256 * 4, st));
     dim3 gfull((B.max_n + BZ_TILE - 1) / BZ_TILE, B.nblk);
     u32 maxch = (B.max_n + CH - 1) / CH;
     dim3 gch((maxch + WPB - 1) / WPB, B.nblk);
-    ctx->prof_begin(K_USED, ne_act); k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK();
+    if (!used_ready) { ctx->prof_begin(K_USED, ne_act); k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK(); }
     ctx->prof_begin(K_MTF_SUMMARY, ne_act * 2); k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
     ctx->prof_begin(K_MTF_SCAN, ne_act * 2); k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
-    ctx->prof_begin(K_MTF_EMIT, ne_act * 3); k_mtf_emit2<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride,
-                                           nch_stride);
+    static const bool use_v2 = getenv("BZ2B200_MTF_V2") != nullptr;
+    ctx->prof_begin(K_MTF_EMIT, ne_act * 3);
+    if (use_v2) k_mtf_emit2<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
+    else k_mtf_emit3<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
     LAUNCH_OK();
     return BZ2B200_OK;
 }
