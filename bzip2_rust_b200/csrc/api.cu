@@ -13,6 +13,9 @@ bz2b200_ctx::~bz2b200_ctx() {
     h_stage.release(); h_small.release(); h_out.release();
     for (int i = 0; i < 8; i++) if (ev[i]) cudaEventDestroy(ev[i]);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : up_ev) cudaEventDestroy(e);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_down) cudaStreamDestroy(s_down);
     if (stream) cudaStreamDestroy(stream);
 }
 

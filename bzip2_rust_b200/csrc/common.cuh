@@ -79,9 +79,21 @@ static const char *const kKernelNames[] = { "k_radix_hist0", "k_radix_scan", "k_
 struct KStat { double ms = 0; u64 launches = 0; u64 bytes = 0; };
 struct PendingEv { int id; u64 bytes; cudaEvent_t a, b; };
 
+// Input that is still arriving on an upload stream (host-buffer entry points): event i fires when stream bytes
+// [0, (i+1)*chunk) are on the device.  bz_rle1_window launches its scan chunk by chunk behind the upload.
+struct Arrival {
+    std::vector<cudaEvent_t> *ev;
+    size_t chunk;
+    size_t win_off;      // stream offset of the window being scanned
+    size_t waited;       // events the compute stream already waits for
+};
+
 struct bz2b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_up = nullptr, s_down = nullptr;      // host-buffer pipelining (stream.cu)
+    std::vector<cudaEvent_t> up_ev;
+    Arrival *arrival = nullptr;
     std::mutex mu;
     std::string err;
     u64 launches = 0;

@@ -577,7 +577,26 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
         BZ_CHECK(cudaMemsetAsync(st1, 0, state_bytes, st));
         ScanArgs sa;
         sa.x = d_x; sa.W = W; sa.RS = RS; sa.OUT = OUT; sa.LASTQ = LASTQ; sa.st1 = st1; sa.st2 = st2; sa.ticket = ticket;
-        ctx->prof_begin(K_RLE_SCAN, (u64)W * 13); k_rle_scan<<<tiles, BZ_THREADS, 0, st>>>(sa); LAUNCH_OK();
+        if (!ctx->arrival) {
+            ctx->prof_begin(K_RLE_SCAN, (u64)W * 13); k_rle_scan<<<tiles, BZ_THREADS, 0, st>>>(sa); LAUNCH_OK();
+        } else {
+            // the window is still being uploaded: scan the tiles of every chunk as it lands (tiles take their index
+            // from the ticket counter, so consecutive launches simply continue; a tile looks 19 bytes ahead)
+            Arrival &A = *ctx->arrival;
+            const size_t nev = A.ev->size();
+            u32 launched = 0;
+            while (launched < tiles) {
+                if (A.waited < nev) { BZ_CHECK(cudaStreamWaitEvent(st, (*A.ev)[A.waited], 0)); A.waited++; }
+                size_t have = A.waited >= nev ? (size_t)-1 : A.waited * A.chunk;     // stream bytes present
+                size_t have_win = have > A.win_off ? have - A.win_off : 0;
+                u32 upto = have_win >= W ? tiles : (have_win > 64 ? (u32)((have_win - 64) / SC_TILE) : 0u);
+                if (upto > launched) {
+                    ctx->prof_begin(K_RLE_SCAN, (u64)(upto - launched) * SC_TILE * 13);
+                    k_rle_scan<<<upto - launched, BZ_THREADS, 0, st>>>(sa); LAUNCH_OK();
+                    launched = upto;
+                }
+            }
+        }
     }
     ChainArgs a;
     a.x = d_x; a.RS = RS; a.OUT = OUT; a.LASTQ = LASTQ; a.W = W; a.B = Bsz; a.is_eof = is_eof ? 1u : 0u;

@@ -6,6 +6,7 @@
 // here every block carries its exact bit length, an exclusive prefix sum gives its absolute bit
 // offset, and one kernel ORs the blocks of a batch into the final buffer at those offsets.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 
@@ -108,13 +109,24 @@ u32 off_from_for(size_t n, int level, size_t window_pos) {
     return abs_from > window_pos ? (u32)std::min<size_t>(abs_from - window_pos, 0xFFFFFFF0u) : 0u;
 }
 
+// Host-buffer pipelining of one bz2b200_compress_stream call: the input arrives in chunks on an upload stream while
+// earlier windows are being compressed, and finished output bytes leave on a download stream.
+struct Pipe {
+    cudaStream_t down;
+    std::vector<cudaEvent_t> *up_ev;   // up_ev[i] fires when input bytes [0, (i+1)*chunk) are on the device
+    size_t chunk;
+    size_t waited;                     // upload events the compute stream already waits for
+    u8 *h_out; size_t out_cap;
+    size_t down_done;                  // output bytes already handed to the download stream
+};
+
 // Core: d_in[0..n) on the device -> d_out (device), both owned by the caller.
 // If block_crcs != nullptr the stream header/footer are omitted and only blocks
 // [first, first+count) of the sequence starting at d_in are emitted (multi-GPU range mode: d_in then
 // points at the first block's first byte and n_is_eof says whether d_in+n is the end of the stream).
 static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, u8 *d_out, size_t out_cap,
                          u64 *out_bits, bool whole_stream, bool n_is_eof, size_t stream_n, size_t stream_pos,
-                         u32 max_count, std::vector<u32> *crcs_out) {
+                         u32 max_count, std::vector<u32> *crcs_out, size_t window = WINDOW, Pipe *pipe = nullptr) {
     cudaStream_t st = ctx->stream;
     if (out_cap < 16) return BZ2B200_E_CAP;
     if (ctx->timing) cudaEventRecord(ctx->ev_total[0], st);
@@ -129,14 +141,21 @@ static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, 
     u32 batch_blocks = (u32)std::min<size_t>(MAX_BATCH_BLOCKS, std::max<size_t>(1, MAX_BATCH_BYTES / stride));
     std::vector<u64> hoff;
     while (pos < n && done_blocks < max_count) {
-        size_t W = std::min(n - pos, WINDOW);
+        size_t W = std::min(n - pos, window);
+        if (n - pos - W < window / 2) W = std::min(n - pos, WINDOW);   // no small tail window
         bool eof = n_is_eof && (pos + W == n);
         Batch B;
         u32 nb = 0, consumed = 0;
         u32 want = std::min(batch_blocks, max_count - done_blocks);
+        Arrival arr;
+        if (pipe) {                                              // the RLE1 scan follows the upload chunk by chunk
+            arr.ev = pipe->up_ev; arr.chunk = pipe->chunk; arr.win_off = pos; arr.waited = pipe->waited;
+            ctx->arrival = &arr;
+        }
         if (ctx->timing) cudaEventRecord(ctx->ev[4], st);
         int rc = bz_rle1_window(ctx, d_in + pos, (u32)W, level, eof, off_from_for(stream_n, level, stream_pos + pos),
                                 want, B, &nb, &consumed, nullptr, false);
+        if (pipe) { pipe->waited = arr.waited; ctx->arrival = nullptr; }
         if (rc) return rc;
         if (ctx->timing) { cudaEventRecord(ctx->ev[5], st); }
         if (nb == 0) { ctx->err = "rle1: window too small for one block"; return BZ2B200_E_ARG; }
@@ -171,6 +190,15 @@ static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, 
         ctx->prof_begin(K_CONCAT, maxbits / 4 * nb); k_concat_bits<<<gc, 256, 0, st>>>(H.d_out, H.out_stride, H.d_bits, ctx->d_bitoff.as<u64>(), (u32 *)d_out);
         LAUNCH_OK();
         BZ_CHECK(cudaStreamSynchronize(st));                    // hoff is reused by the next batch
+        if (pipe) {                                              // whole words below the bit position are final
+            size_t fin = (size_t)(bitpos / 32) * 4;
+            if (fin > pipe->out_cap) return BZ2B200_E_CAP;
+            if (fin > pipe->down_done) {
+                BZ_CHECK(cudaMemcpyAsync(pipe->h_out + pipe->down_done, d_out + pipe->down_done, fin - pipe->down_done,
+                                         cudaMemcpyDeviceToHost, pipe->down));
+                pipe->down_done = fin;
+            }
+        }
         pos += consumed;
         done_blocks += nb;
     }
@@ -216,18 +244,49 @@ int bz2b200_compress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int l
     if (!ctx || (!in && n) || !out || !out_len || level < 1 || level > 9) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
-    int rc = upload(ctx, in, n, ctx->d_in);
-    if (rc) return rc;
+    // knobs: windows per call (1 = upload everything, compress, download) and upload chunk size
+    static const int n_windows = [] { const char *e = getenv("BZ2B200_E2E_WINDOWS"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    const size_t CHUNK = 8u << 20;
     size_t cap = bz2b200_compress_bound(n);
+    BZ_CHECK(ctx->d_in.ensure(n + 64));
     BZ_CHECK(ctx->d_stream.ensure(cap + 64));
+    if (!ctx->s_up) {
+        BZ_CHECK(cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
+        BZ_CHECK(cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
+    }
+    size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    while (ctx->up_ev.size() < nchunks) {
+        cudaEvent_t e;
+        BZ_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->up_ev.push_back(e);
+    }
+    std::vector<cudaEvent_t> evs(ctx->up_ev.begin(), ctx->up_ev.begin() + nchunks);
+    for (size_t i = 0; i < nchunks; i++) {
+        size_t off = i * CHUNK, len = std::min(CHUNK, n - off);
+        BZ_CHECK(cudaMemcpyAsync(ctx->d_in.as<u8>() + off, in + off, len, cudaMemcpyHostToDevice, ctx->s_up));
+        BZ_CHECK(cudaEventRecord(evs[i], ctx->s_up));
+    }
+    Pipe pipe;
+    pipe.down = ctx->s_down; pipe.up_ev = &evs; pipe.chunk = CHUNK; pipe.waited = 0;
+    pipe.h_out = out; pipe.out_cap = out_cap; pipe.down_done = 0;
+    // windows of whole MiB, at least 16 MiB each: small windows leave the GPU under-filled
+    size_t window = WINDOW;
+    if (n_windows > 1 && n > (32u << 20)) {
+        window = std::max<size_t>(n / n_windows + (1u << 20), 16u << 20) & ~(size_t)0xFFFFF;
+        if (window > WINDOW) window = WINDOW;
+    }
     u64 bits = 0;
-    rc = compress_core(ctx, ctx->d_in.as<u8>(), n, level, ctx->d_stream.as<u8>(), cap & ~(size_t)3, &bits, true, true, n, 0,
-                       0xFFFFFFFFu, nullptr);
-    if (rc) return rc;
+    int rc = compress_core(ctx, ctx->d_in.as<u8>(), n, level, ctx->d_stream.as<u8>(), cap & ~(size_t)3, &bits, true, true, n, 0,
+                           0xFFFFFFFFu, nullptr, window, &pipe);
+    if (rc) { cudaStreamSynchronize(ctx->s_up); cudaStreamSynchronize(ctx->s_down); return rc; }
     size_t len = (size_t)((bits + 7) / 8);
-    if (len > out_cap) return BZ2B200_E_CAP;
-    BZ_CHECK(cudaMemcpyAsync(out, ctx->d_stream.p, len, cudaMemcpyDeviceToHost, ctx->stream));
-    BZ_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (len > out_cap) { cudaStreamSynchronize(ctx->s_down); return BZ2B200_E_CAP; }
+    if (len > pipe.down_done)
+        BZ_CHECK(cudaMemcpyAsync(out + pipe.down_done, ctx->d_stream.as<u8>() + pipe.down_done, len - pipe.down_done,
+                                 cudaMemcpyDeviceToHost, ctx->s_down));
+    // the stream header is written together with the footer, after the first words may already have left
+    if (pipe.down_done) BZ_CHECK(cudaMemcpyAsync(out, ctx->d_stream.p, std::min<size_t>(4, len), cudaMemcpyDeviceToHost, ctx->s_down));
+    BZ_CHECK(cudaStreamSynchronize(ctx->s_down));
     *out_len = len;
     return BZ2B200_OK;
 }
