@@ -6,9 +6,9 @@
 // The reference decodes one block after another on one thread; blocks are independent once their
 // start bits are known, so:
 //   k_dec_find_magic  every bit offset is tested for the 48-bit block / footer magic
-//   k_dec_block       one CTA per block, one lane walks the entropy-coded part: symbol map, selectors
-//                     (unary + inverse MTF), code lengths (5-bit origin + deltas), canonical decode
-//                     tables, Huffman decode, inverse MTF + RUNA/RUNB expansion -> BWT string
+//   decode4.cuh       entropy decode, parallel inside a block: header -> tables, a lengths-only walk for the
+//                     bit offset of every 50-symbol group, one thread per group for the symbols, inverse MTF +
+//                     RUNA/RUNB by chunks whose start lists come from composing per-chunk permutations
 //   inverse BWT       stable counting sort of rows by byte = one pass of the BWT stage's radix kernels
 //                     (P[j] = row of the j-th smallest byte), then the n-step pointer chase of
 //                     bwt_decode is cut into ~n/256 segments at splitter rows: k_ibwt_chase measures
@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "radix.cuh"
 #include <algorithm>
+#include <stddef.h>
 #include <string.h>
 
 int bz_crc_spans_dev(bz2b200_ctx *ctx, const u8 *d_x, const u32 *d_se /* [nb][2] */, u32 nb, u32 max_span,
@@ -31,11 +32,6 @@ namespace {
 constexpr u64 MAGIC_BLOCK = 0x314159265359ull;
 constexpr u64 MAGIC_END = 0x177245385090ull;
 constexpr int SPLIT = 256;               // inverse BWT: one splitter row every SPLIT rows
-
-struct DecBlock {          // per block, filled by k_dec_block
-    u32 crc, key, nblock, status;        // status 0 = ok
-    u64 end_bit;                         // bit position after the EOB code
-};
 
 __device__ __forceinline__ u64 load_be64(const u8 *p, size_t n, size_t byte) {
     u64 v = 0;
@@ -59,120 +55,6 @@ __global__ void __launch_bounds__(256) k_dec_find_magic(const u8 *in, size_t n, 
             if (k < cap) cand[k] = ((u64)byte * 8 + sh) | (m == MAGIC_END ? (1ull << 63) : 0);
         }
     }
-}
-
-struct BitRd {
-    const u8 *p; size_t n; u64 pos;      // absolute bit position
-    __device__ u32 get(int k) {          // k <= 24
-        if (k == 0) return 0;
-        size_t byte = (size_t)(pos >> 3);
-        u32 w = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) w = (w << 8) | (byte + i < n ? p[byte + i] : 0);
-        u32 v = (w << (pos & 7)) >> (32 - k);
-        pos += k;
-        return v;
-    }
-    __device__ u32 bit() { size_t byte = (size_t)(pos >> 3); u32 v = byte < n ? (p[byte] >> (7 - (pos & 7))) & 1 : 0; pos++; return v; }
-};
-
-// one CTA (32 threads) per block; lane 0 decodes
-__global__ void __launch_bounds__(32) k_dec_block(const u8 *in, size_t n, const u64 *start_bits, u32 max_block,
-                                                  u8 *tt_all, u32 stride, u8 *sel_all, u32 sel_stride, DecBlock *out) {
-    u32 b = blockIdx.x;
-    __shared__ u8 len[6][258];
-    __shared__ u16 perm[6][258];
-    __shared__ int limit[6][22], base[6][22];
-    __shared__ int minl[6];
-    __shared__ u8 seq[256];
-    if (threadIdx.x != 0) return;
-    DecBlock r; r.status = 0; r.nblock = 0; r.end_bit = 0;
-    BitRd br{in, n, start_bits[b] + 48};
-    u8 *tt = tt_all + (size_t)b * stride;
-    u8 *sel = sel_all + (size_t)b * sel_stride;
-    { u32 hi16 = br.get(16); u32 lo16 = br.get(16); r.crc = (hi16 << 16) | lo16; }
-    if (br.bit()) { r.status = 1; out[b] = r; return; }        // randomised blocks: not produced by this encoder
-    r.key = br.get(24);
-    u32 l1 = br.get(16);
-    int nused = 0;
-    for (int i = 0; i < 16; i++) if (l1 & (0x8000u >> i)) {
-        u32 l2 = br.get(16);
-        for (int j = 0; j < 16; j++) if (l2 & (0x8000u >> j)) seq[nused++] = (u8)(i * 16 + j);
-    }
-    if (nused == 0) { r.status = 2; out[b] = r; return; }
-    int alpha = nused + 2;
-    int T = (int)br.get(3);
-    u32 G = br.get(15);
-    if (T < 2 || T > 6 || G < 1 || G > sel_stride) { r.status = 3; out[b] = r; return; }
-    {   // selectors: unary index into an MTF list of table numbers (decompress.rs:140-203)
-        u8 l6[6] = {0, 1, 2, 3, 4, 5};
-        for (u32 g = 0; g < G; g++) {
-            int j = 0;
-            while (br.bit()) { j++; if (j >= T) { r.status = 4; out[b] = r; return; } }
-            u8 v = l6[j];
-            for (int k = j; k > 0; k--) l6[k] = l6[k - 1];
-            l6[0] = v;
-            sel[g] = v;
-        }
-    }
-    for (int t = 0; t < T; t++) {        // code lengths (decompress.rs:216-260)
-        int c = (int)br.get(5);
-        for (int s = 0; s < alpha; s++) {
-            for (;;) {
-                if (c < 1 || c > 20) { r.status = 5; out[b] = r; return; }
-                if (!br.bit()) break;
-                c += br.bit() ? -1 : 1;
-            }
-            len[t][s] = (u8)c;
-        }
-    }
-    for (int t = 0; t < T; t++) {        // canonical decode tables (huf_decode_map, decompress.rs:426-486)
-        int mn = 32, mx = 0;
-        for (int s = 0; s < alpha; s++) { int l = len[t][s]; mn = min(mn, l); mx = max(mx, l); }
-        minl[t] = mn;
-        int pp = 0;
-        for (int l = mn; l <= mx; l++) for (int s = 0; s < alpha; s++) if (len[t][s] == l) perm[t][pp++] = (u16)s;
-        int cnt[22];
-        for (int l = 0; l < 22; l++) cnt[l] = 0;
-        for (int s = 0; s < alpha; s++) cnt[len[t][s]]++;
-        int code = 0, idx = 0;
-        for (int l = 1; l <= 20; l++) {
-            base[t][l] = idx - code; code += cnt[l]; idx += cnt[l]; limit[t][l] = code - 1; code <<= 1;
-        }
-        for (int l = 1; l <= 20; l++) if (l > mx) limit[t][l] = 0x7fffffff;
-    }
-    // Huffman decode + inverse MTF/RLE2 (decompress.rs:293-358, rle2_mtf.rs:191-287)
-    u32 nblk = 0, runlen = 0, runbit = 1, g = 0, gpos = 50;
-    int t = 0;
-    for (;;) {
-        if (gpos == 50) { if (g >= G) { r.status = 6; break; } t = sel[g++]; gpos = 0; }
-        gpos++;
-        int l = minl[t];
-        int code = (int)br.get(l);
-        while (l <= 20 && code > limit[t][l]) { l++; code = (code << 1) | (int)br.bit(); }
-        if (l > 20 || (br.pos >> 3) > n + 4) { r.status = 7; break; }
-        int pi = code + base[t][l];
-        if (pi < 0 || pi >= alpha) { r.status = 8; break; }
-        u32 s = perm[t][pi];
-        if (s <= 1) { runlen += runbit << s; runbit <<= 1; if (runlen > max_block) { r.status = 9; break; } continue; }
-        if (runlen) {
-            if (nblk + runlen > max_block) { r.status = 9; break; }
-            u8 c = seq[0];
-            for (u32 k = 0; k < runlen; k++) tt[nblk + k] = c;
-            nblk += runlen; runlen = 0;
-        }
-        runbit = 1;
-        if ((int)s == alpha - 1) break;                            // EOB
-        u8 v = seq[s - 1];
-        for (int k = (int)s - 1; k > 0; k--) seq[k] = seq[k - 1];
-        seq[0] = v;
-        if (nblk + 1 > max_block) { r.status = 9; break; }
-        tt[nblk++] = v;
-    }
-    r.nblock = nblk;
-    r.end_bit = br.pos;
-    if (r.status == 0 && (nblk == 0 || r.key >= nblk)) r.status = 10;
-    out[b] = r;
 }
 
 // ---- inverse BWT ------------------------------------------------------------------------------
@@ -237,42 +119,8 @@ __global__ void __launch_bounds__(256) k_ibwt_write(const u32 *P, const u8 *L, c
     } while (!is_split(row, key) && off < n);
 }
 
-// ---- inverse RLE1 -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_dec_rle1_count(const u8 *blk, const u32 *len, u32 stride, u64 *outlen) {
-    u32 b = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    const u8 *r = blk + (size_t)b * stride;
-    u32 n = len[b];
-    u64 o = 0; int run = 0; int prev = -1;
-    for (u32 i = 0; i < n; i++) {
-        u8 c = r[i];
-        if (run == 4) { o += c; run = 0; prev = -1; continue; }
-        if ((int)c == prev) run++; else { run = 1; prev = c; }
-        o++;
-    }
-    outlen[b] = o;
-}
-__global__ void __launch_bounds__(32) k_dec_rle1_write(const u8 *blk, const u32 *len, u32 stride, const u64 *outoff, u8 *out) {
-    u32 b = blockIdx.x;
-    const u8 *r = blk + (size_t)b * stride;
-    u32 n = len[b];
-    u8 *o = out + outoff[b];
-    int lane = threadIdx.x;
-    u64 w = 0; int run = 0; int prev = -1;
-    for (u32 i = 0; i < n; i++) {
-        u8 c = r[i];
-        if (run == 4) {                       // repeat count: the warp fills it cooperatively
-            for (u32 k = lane; k < c; k += 32) o[w + k] = (u8)prev;
-            w += c; run = 0; prev = -1; continue;
-        }
-        if ((int)c == prev) run++; else { run = 1; prev = c; }
-        if (lane == 0) o[w] = c;
-        w++;
-    }
-}
-
-#include "decode2.cuh"   // k_dec_block2 (superseded), k_rle1_inv
-#include "decode3.cuh"   // k_dec_block3: the entropy decoder that is launched
+#include "decode4.cuh"       // entropy decode: header, group boundaries, symbols, chunked inverse MTF
+#include "decode_rle1.cuh"   // k_rle1_inv
 
 }  // namespace
 
@@ -376,26 +224,52 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
         stored_combined = (u32)((w >> (8 - sh)) & 0xffffffffull);
     }
     if (nb == 0) { *out_len = 0; return stored_combined == 0 ? BZ2B200_OK : BZ2B200_E_CRC; }
-    // ---- 2. entropy decode, one CTA per block ----
+    // ---- 2. entropy decode (decode4.cuh) ----
     u32 max_block = (u32)level * 100000u;
     u32 stride = ((max_block + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE;
     u32 sel_stride = max_block / 50 + 8;
+    u32 max_sym = max_block + 2;                                 // every symbol but EOB yields at least one byte
+    u32 sym_stride = ((max_sym + 64 + DCH - 1) / DCH) * DCH;
+    u32 ch_stride = sym_stride / DCH + 2;
     BZ_CHECK(ctx->d_T.ensure((size_t)nb * stride + 64));
     BZ_CHECK(ctx->d_bwt.ensure((size_t)nb * stride + 64));
     BZ_CHECK(ctx->d_sel.ensure((size_t)nb * sel_stride));
-    BZ_CHECK(ctx->d_dec3.ensure((size_t)nb * (sizeof(DecBlock) + 8 + 4 + 4 + 8 + 8 + 8) + 256));
+    BZ_CHECK(ctx->d_gbits.ensure((size_t)nb * sel_stride * 4));
+    BZ_CHECK(ctx->d_sym.ensure((size_t)nb * sym_stride * 2));
+    BZ_CHECK(ctx->d_mtfstate.ensure((size_t)nb * ch_stride * 256));
+    BZ_CHECK(ctx->d_chunkrec.ensure((size_t)nb * ch_stride * 8));
+    BZ_CHECK(ctx->d_hdr.ensure((size_t)nb * sizeof(DecTables)));
+    BZ_CHECK(ctx->d_dec3.ensure((size_t)nb * (8 + 4 + 4 + 8 + 8 + 8) + 256));
+    DecTables *d_tabs = ctx->d_hdr.as<DecTables>();
+    u32 *d_gbit = ctx->d_gbits.as<u32>();
+    u16 *d_sym = ctx->d_sym.as<u16>();
+    u8 *d_lists = ctx->d_mtfstate.as<u8>();
+    u32 *d_ccount = ctx->d_chunkrec.as<u32>();
+    u32 *d_coff = d_ccount + (size_t)nb * ch_stride;
     u64 *d_starts = ctx->d_dec3.as<u64>();
-    DecBlock *d_db = (DecBlock *)(d_starts + nb);
-    u32 *d_len = (u32 *)(d_db + nb);
+    u32 *d_len = (u32 *)(d_starts + nb);
     const u32 nbp = (nb + 1) & ~1u;                              // keep the u64 arrays 8-byte aligned
     u32 *d_keys = d_len + nbp;
     u64 *d_olen = (u64 *)(d_keys + nbp);
     u64 *d_ooff = d_olen + nb;
     u32 *d_se = (u32 *)(d_ooff + nb);
+    const u8 *d_bits = ctx->d_in.as<u8>();
     BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_BLOCK, n); k_dec_block3<<<nb, 32, 0, st>>>(ctx->d_in.as<u8>(), n, d_starts, max_block, ctx->d_T.as<u8>(), stride, ctx->d_sel.as<u8>(), sel_stride, d_db); LAUNCH_OK();
-    std::vector<DecBlock> db(nb);
-    BZ_CHECK(cudaMemcpyAsync(db.data(), d_db, (size_t)nb * sizeof(DecBlock), cudaMemcpyDeviceToHost, st));
+    ctx->prof_begin(K_DEC_HEADER, 0); k_dec_header<<<nb, 32, 0, st>>>(d_bits, n, d_starts, ctx->d_sel.as<u8>(), sel_stride, d_tabs); LAUNCH_OK();
+    if (!ctx->dec_attr_done) { BZ_CHECK(cudaFuncSetAttribute(k_dec_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BoundsSmem))); ctx->dec_attr_done = true; }
+    ctx->prof_begin(K_DEC_BOUNDS, n); k_dec_bounds<<<nb, 32, sizeof(BoundsSmem), st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, max_sym); LAUNCH_OK();
+    dim3 gs((sel_stride + 127) / 128, nb);
+    ctx->prof_begin(K_DEC_SYMS, n); k_dec_syms<<<gs, 128, 0, st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, d_sym, sym_stride); LAUNCH_OK();
+    dim3 gch((ch_stride + 7) / 8, nb);
+    ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<0><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_CHUNK_SCAN, 0); k_dec_chunk_scan<<<nb, 256, 0, st>>>(d_tabs, d_lists, d_ccount, d_coff, ch_stride, max_block); LAUNCH_OK();
+    ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<1><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
+    // per-block results: the tail of DecTables (T .. pad)
+    struct DecTail { u32 T, alpha, G, status, crc, key; u64 data_bit, end_bit; u32 nsym, ngroups, nblock, pad; };
+    static_assert(sizeof(DecTail) == sizeof(DecTables) - offsetof(DecTables, T), "DecTail mirrors the tail of DecTables");
+    std::vector<DecTail> db(nb);
+    BZ_CHECK(cudaMemcpy2DAsync(db.data(), sizeof(DecTail), (const u8 *)d_tabs + offsetof(DecTables, T), sizeof(DecTables),
+                               sizeof(DecTail), nb, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
     std::vector<u32> hlen(nb), hkey(nb);
     u32 combined = 0, max_n = 0; u64 total_n = 0;

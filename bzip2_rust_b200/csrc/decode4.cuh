@@ -1,0 +1,522 @@
+// decode4.cuh -- entropy decoding of all blocks of a stream, parallel INSIDE a block (included by decode.cu).
+//
+// Replaces the per-block loop of decompress (reference src/compression/decompress.rs:98-358) and
+// rle2_mtf_decode_fast (src/tools/rle2_mtf.rs:191-287).  The earlier versions walked a block with one warp
+// (Huffman decode and MTF replay symbol by symbol): 160 ms for 112 blocks, the GPU empty.  A bzip2 block has two
+// serial dependences -- where each Huffman code starts, and the MTF list -- and both are cut here:
+//   k_dec_header   one warp per block: symbol map, selectors, code lengths -> canonical tables + 10-bit LUTs
+//   k_dec_bounds   one lane per block walks the bit stream decoding only code LENGTHS (LUT probe, skip) and
+//                  records the bit offset of every 50-symbol group: the only sequential pass left
+//   k_dec_syms     one thread per group decodes its 50 symbols from that offset with the group's table
+//   k_dec_chunks<0> one warp per ~1024-symbol chunk (cut where no RUNA/RUNB run is open): bytes the chunk
+//                  produces, and the PERMUTATION its MTF ranks apply to the list (replayed on the identity)
+//   k_dec_chunk_scan one CTA per block: composes the permutations in order -> the MTF list at every chunk
+//                  start, and the output offset of every chunk
+//   k_dec_chunks<1> the same walk with the real list: inverse MTF + RUNA/RUNB expansion -> the BWT string
+
+constexpr int LUTBITS = 10;
+constexpr int DCH = 1024;              // nominal symbols per MTF chunk
+
+struct DecTables {                     // per block, global memory
+    u16 lut[6][1 << LUTBITS];          // (code length << 9) | symbol; 0 = longer than LUTBITS
+    u16 perm[6][258];
+    int limit[6][22], base[6][22];
+    u8 seq[256];                       // used byte values ascending = initial MTF list
+    u32 T, alpha, G, status;
+    u32 crc, key;
+    u64 data_bit;                      // first bit of the symbol data
+    u64 end_bit;                       // bit after the EOB code            (k_dec_bounds)
+    u32 nsym, ngroups;                 // symbols incl. EOB, groups in use  (k_dec_bounds)
+    u32 nblock, pad;                   // decoded BWT string length          (k_dec_chunk_scan)
+};
+
+struct BitBuf {
+    const u8 *p; size_t n; size_t byte;      // next byte to load
+    u64 buf; int nb;                         // `nb` valid bits, MSB aligned
+    __device__ void init(const u8 *in, size_t len, u64 bitpos) {
+        p = in; n = len; byte = (size_t)(bitpos >> 3); buf = 0; nb = 0;
+        refill();
+        int sk = (int)(bitpos & 7);
+        buf <<= sk; nb -= sk;
+    }
+    __device__ __forceinline__ void refill() {
+        while (nb <= 32) {
+            u32 w;
+            if (byte + 4 <= n) {
+                w = ((u32)p[byte] << 24) | ((u32)p[byte + 1] << 16) | ((u32)p[byte + 2] << 8) | (u32)p[byte + 3];
+            } else {
+                w = 0;
+                for (int k = 0; k < 4; k++) w = (w << 8) | (byte + k < n ? p[byte + k] : 0);
+            }
+            byte += 4;
+            buf |= (u64)w << (32 - nb);
+            nb += 32;
+        }
+    }
+    __device__ __forceinline__ u32 peek(int k) const { return (u32)(buf >> (64 - k)); }     // 1 <= k <= 32
+    __device__ __forceinline__ void skip(int k) { buf <<= k; nb -= k; }
+    __device__ __forceinline__ u32 get(int k) { if (k == 0) return 0; refill(); u32 v = peek(k); skip(k); return v; }
+    __device__ u64 bitpos() const { return (u64)byte * 8 - (u64)nb; }
+};
+
+// Bit reader over 4-byte aligned words with the next word already in flight (the walk of k_dec_bounds is one
+// long dependent chain: a load issued when it is needed would add its latency to every sixth symbol).
+struct WordBits {
+    const u32 *w; size_t nw, idx;            // idx = next word to fetch into `ahead`
+    u64 buf; int nb; u32 ahead;
+    __device__ __forceinline__ u32 fetch(size_t i) const { return i < nw ? __byte_perm(__ldg(w + i), 0, 0x0123) : 0u; }
+    __device__ void init(const u8 *in, size_t len, u64 bitpos) {     // `in` is 4-byte aligned, len padded reads are safe
+        w = (const u32 *)in; nw = (len + 3) / 4;
+        size_t first = (size_t)(bitpos >> 5);
+        buf = ((u64)fetch(first) << 32) | fetch(first + 1);
+        nb = 64;
+        idx = first + 3; ahead = fetch(first + 2);
+        int sk = (int)(bitpos & 31);
+        buf <<= sk; nb -= sk;
+    }
+    __device__ __forceinline__ void refill() {
+        if (nb <= 32) {
+            buf |= (u64)ahead << (32 - nb);
+            nb += 32;
+            size_t i = idx < nw ? idx : nw - 1;                  // clamped: a corrupt stream must not walk off the buffer
+            ahead = __byte_perm(__ldg(w + i), 0, 0x0123); idx++;
+            size_t pf = idx + 48 < nw ? idx + 48 : nw - 1;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(w + pf));
+        }
+    }
+    __device__ __forceinline__ u32 peek(int k) const { return (u32)(buf >> (64 - k)); }
+    __device__ __forceinline__ void skip(int k) { buf <<= k; nb -= k; }
+    __device__ u64 bitpos() const { return (u64)(idx - 1) * 32 - (u64)nb; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// header: decompress.rs:98-260 + huf_decode_map (:426-486)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const u64 *start_bits, u8 *sel_all,
+                                                   u32 sel_stride, DecTables *tabs) {
+    u32 b = blockIdx.x;
+    __shared__ u8 len[6][258];
+    __shared__ u16 perm[6][258];
+    __shared__ int limit[6][22], base[6][22];
+    __shared__ u16 lut[6][1 << LUTBITS];
+    __shared__ u8 seq[256];
+    __shared__ int s_T, s_alpha, s_status;
+    __shared__ u32 s_G, s_crc, s_key;
+    __shared__ u64 s_data;
+    const int lane = threadIdx.x;
+    u8 *sel = sel_all + (size_t)b * sel_stride;
+    for (int i = lane; i < 256; i += 32) seq[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        BitBuf br;
+        s_status = 0;
+        br.init(in, n, start_bits[b] + 48);
+        { u32 hi16 = br.get(16); u32 lo16 = br.get(16); s_crc = (hi16 << 16) | lo16; }
+        if (br.get(1)) s_status = 1;                            // randomised blocks: not produced by this encoder
+        s_key = br.get(24);
+        u32 l1 = br.get(16);
+        int nused = 0;
+        for (int i = 0; i < 16; i++) if (l1 & (0x8000u >> i)) {
+            u32 l2 = br.get(16);
+            for (int j = 0; j < 16; j++) if (l2 & (0x8000u >> j)) seq[nused++] = (u8)(i * 16 + j);
+        }
+        if (nused == 0 && !s_status) s_status = 2;
+        int alpha = nused + 2;
+        int T = (int)br.get(3);
+        u32 G = br.get(15);
+        if (!s_status && (T < 2 || T > 6 || G < 1 || G > sel_stride)) s_status = 3;
+        if (!s_status) {                                        // selectors: unary index into an MTF list (decompress.rs:140-203)
+            u8 l6[6] = {0, 1, 2, 3, 4, 5};
+            for (u32 g = 0; g < G && !s_status; g++) {
+                int j = 0;
+                while (br.get(1)) { j++; if (j >= T) { s_status = 4; break; } }
+                if (s_status) break;
+                u8 v = l6[j];
+                for (int k = j; k > 0; k--) l6[k] = l6[k - 1];
+                l6[0] = v;
+                sel[g] = v;
+            }
+        }
+        for (int t = 0; t < T && !s_status; t++) {             // code lengths (decompress.rs:216-260)
+            int c = (int)br.get(5);
+            for (int s = 0; s < alpha && !s_status; s++) {
+                for (;;) {
+                    if (c < 1 || c > 20) { s_status = 5; break; }
+                    if (!br.get(1)) break;
+                    c += br.get(1) ? -1 : 1;
+                }
+                len[t][s] = (u8)c;
+            }
+        }
+        s_T = T; s_alpha = alpha; s_G = G; s_data = br.bitpos();
+    }
+    __syncwarp();
+    const int T = s_T, alpha = s_alpha;
+    if (s_status == 0) {
+        if (lane < T) {
+            int t = lane;
+            int mn = 32, mx = 0;
+            for (int s = 0; s < alpha; s++) { int l = len[t][s]; mn = min(mn, l); mx = max(mx, l); }
+            int pp = 0;
+            for (int l = mn; l <= mx; l++) for (int s = 0; s < alpha; s++) if (len[t][s] == l) perm[t][pp++] = (u16)s;
+            int cnt[22];
+            for (int l = 0; l < 22; l++) cnt[l] = 0;
+            for (int s = 0; s < alpha; s++) cnt[len[t][s]]++;
+            int code = 0, idx = 0;
+            for (int l = 1; l <= 20; l++) {
+                base[t][l] = idx - code; code += cnt[l]; idx += cnt[l]; limit[t][l] = code - 1; code <<= 1;
+            }
+            for (int l = 1; l <= 20; l++) if (l > mx) limit[t][l] = 0x7fffffff;
+            limit[t][0] = -1; limit[t][21] = 0x7fffffff; base[t][0] = 0; base[t][21] = 0;
+        }
+        for (int i = lane; i < 6 * (1 << LUTBITS); i += 32) (&lut[0][0])[i] = 0;
+        __syncwarp();
+        for (int t = 0; t < T; t++) {
+            for (int pi = lane; pi < alpha; pi += 32) {
+                int s = perm[t][pi];
+                int l = len[t][s];
+                if (l <= LUTBITS) {
+                    int code = pi - base[t][l];
+                    int lo = code << (LUTBITS - l), hi = lo + (1 << (LUTBITS - l));
+                    u16 e = (u16)((l << 9) | s);
+                    for (int k = lo; k < hi && k < (1 << LUTBITS); k++) lut[t][k] = e;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    DecTables *o = tabs + b;
+    for (int i = lane; i < 6 * (1 << LUTBITS); i += 32) (&o->lut[0][0])[i] = (&lut[0][0])[i];
+    for (int i = lane; i < 6 * 258; i += 32) (&o->perm[0][0])[i] = (&perm[0][0])[i];
+    for (int i = lane; i < 6 * 22; i += 32) { (&o->limit[0][0])[i] = (&limit[0][0])[i]; (&o->base[0][0])[i] = (&base[0][0])[i]; }
+    for (int i = lane; i < 256; i += 32) o->seq[i] = seq[i];
+    if (lane == 0) {
+        o->T = (u32)T; o->alpha = (u32)alpha; o->G = s_G; o->status = (u32)s_status; o->crc = s_crc; o->key = s_key;
+        o->data_bit = s_data; o->end_bit = 0; o->nsym = 0; o->ngroups = 0; o->nblock = 0; o->pad = 0;
+    }
+}
+
+// shared copy of the decode tables of one block (all threads of the CTA call)
+struct SmemTables {
+    u16 lut[6][1 << LUTBITS];
+    u16 perm[6][258];
+    int limit[6][22], base[6][22];
+};
+__device__ __forceinline__ void load_tables(SmemTables &s, const DecTables *g) {
+    for (int i = threadIdx.x; i < 6 * (1 << LUTBITS) / 2; i += blockDim.x) ((u32 *)&s.lut[0][0])[i] = ((const u32 *)&g->lut[0][0])[i];
+    for (int i = threadIdx.x; i < 6 * 258 / 2; i += blockDim.x) ((u32 *)&s.perm[0][0])[i] = ((const u32 *)&g->perm[0][0])[i];
+    for (int i = threadIdx.x; i < 6 * 22; i += blockDim.x) { (&s.limit[0][0])[i] = (&g->limit[0][0])[i]; (&s.base[0][0])[i] = (&g->base[0][0])[i]; }
+}
+
+// one Huffman symbol with table t; returns the symbol, or -1 on a malformed code.  R = BitBuf or WordBits.
+template <class R>
+__device__ __forceinline__ int decode_one(R &br, const SmemTables &s, int t, int alpha) {
+    br.refill();
+    u16 e = s.lut[t][br.peek(LUTBITS)];
+    if (e) { br.skip(e >> 9); return (int)(e & 511u); }
+    int l = LUTBITS + 1;
+    int code = (int)br.peek(l);
+    while (l <= 20 && code > s.limit[t][l]) { l++; code = (int)br.peek(l); }
+    if (l > 20) return -1;
+    int pi = code + s.base[t][l];
+    if (pi < 0 || pi >= alpha) return -1;
+    br.skip(l);
+    return (int)s.perm[t][pi];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// group boundaries: the one sequential walk (decompress.rs:293-358 without the symbol work)
+// ---------------------------------------------------------------------------------------------------------
+// The walk is one dependent chain per block (probe, shift, probe ...), ~150 cycles per symbol with a one-symbol
+// table.  A 12-bit window usually holds TWO codes, so the pair table below halves the chain.
+// entry: [4:0] length of both codes if two fit (else 0), [9:5] length of the first code (0 = longer than 12 bits),
+// bit 10 = the first symbol is EOB, bit 11 = the second is, bit 12 = "special" (any of: long code, EOB): the walk
+// takes one rarely-taken branch per probe, everything else is selects (a lone warp pays ~20 cycles per branch).
+constexpr int PAIRBITS = 12;
+struct BoundsSmem {
+    u16 pair[6][1 << PAIRBITS];
+    u16 perm[6][258];
+    int limit[6][22], base[6][22];
+};
+
+// canonical decode of the code at the top of the left-aligned `win` (valid bits: `avail`); returns length or 0
+__device__ __forceinline__ int canon_len(const DecTables *g, int t, u32 win, int avail, int alpha, int &sym) {
+    for (int l = 1; l <= 20 && l <= avail; l++) {
+        int code = (int)(win >> (32 - l));
+        if (code <= g->limit[t][l]) {
+            int pi = code + g->base[t][l];
+            if (pi < 0 || pi >= alpha) return 0;
+            sym = g->perm[t][pi];
+            return l;
+        }
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(32) k_dec_bounds(const u8 *in, size_t n, const u8 *sel_all, u32 sel_stride,
+                                                   DecTables *tabs, u32 *gbit_all, u32 max_sym) {
+    u32 b = blockIdx.x;
+    extern __shared__ __align__(16) unsigned char bounds_smem[];
+    BoundsSmem &st = *(BoundsSmem *)bounds_smem;
+    DecTables *tb = tabs + b;
+    if (tb->status) return;
+    const int alpha = (int)tb->alpha;
+    const int T = (int)tb->T;
+    for (int i = threadIdx.x; i < 6 * 258; i += 32) (&st.perm[0][0])[i] = (&tb->perm[0][0])[i];
+    for (int i = threadIdx.x; i < 6 * 22; i += 32) { (&st.limit[0][0])[i] = (&tb->limit[0][0])[i]; (&st.base[0][0])[i] = (&tb->base[0][0])[i]; }
+    for (int t = 0; t < T; t++) {
+        for (int v = threadIdx.x; v < (1 << PAIRBITS); v += 32) {
+            u32 win = (u32)v << (32 - PAIRBITS);
+            int s1 = 0, s2 = 0;
+            int l1 = canon_len(tb, t, win, PAIRBITS, alpha, s1);
+            u32 e = 0x1000u;
+            if (l1) {
+                e = (u32)l1 << 5;
+                if (s1 == alpha - 1) e |= 0x1400u;
+                else if (l1 < PAIRBITS) {
+                    int l2 = canon_len(tb, t, win << l1, PAIRBITS - l1, alpha, s2);
+                    if (l2) { e |= (u32)(l1 + l2); if (s2 == alpha - 1) e |= 0x1800u; }
+                }
+            }
+            st.pair[t][v] = (u16)e;
+        }
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const u8 *sel = sel_all + (size_t)b * sel_stride;
+    u32 *gbit = gbit_all + (size_t)b * sel_stride;
+    const u32 G = tb->G;
+    const u64 data_bit = tb->data_bit;
+    WordBits br;
+    br.init(in, n, data_bit);
+    u32 g = 0, nsym = 0, status = 0;
+    bool done = false;
+    while (!done) {
+        if (g >= G) { status = 6; break; }                      // ran out of selectors before EOB
+        const u16 *pt = st.pair[sel[g]];
+        const int t = sel[g];
+        gbit[g] = (u32)(br.bitpos() - data_bit);
+        g++;
+        int rem = 50;
+        do {
+            br.refill();
+            u32 e = pt[br.peek(PAIRBITS)];
+            if (e & 0x1000u) {                                  // rare: EOB in the window, or a code longer than 12 bits
+                u32 l1 = (e >> 5) & 31u;
+                if (l1 == 0) {
+                    int l = PAIRBITS + 1;
+                    int code = (int)br.peek(l);
+                    while (l <= 20 && code > st.limit[t][l]) { l++; code = (int)br.peek(l); }
+                    int pi = l <= 20 ? code + st.base[t][l] : -1;
+                    if (pi < 0 || pi >= alpha) { status = 7; done = true; break; }
+                    br.skip(l);
+                    nsym++; rem--;
+                    if ((int)st.perm[t][pi] == alpha - 1) { done = true; break; }
+                    continue;
+                }
+                if (e & 0x400u) { br.skip((int)l1); nsym++; done = true; break; }      // the first symbol is EOB
+                if (rem >= 2) { br.skip((int)(e & 31u)); nsym += 2; done = true; break; }   // the second one is
+                br.skip((int)l1); nsym++; rem--;                // EOB is the second symbol but belongs to the next group
+                continue;
+            }
+            const bool two = (e & 31u) != 0 && rem >= 2;
+            br.skip((int)(two ? (e & 31u) : (e >> 5)));
+            const int c = two ? 2 : 1;
+            nsym += c; rem -= c;
+        } while (rem > 0);
+        if (nsym > max_sym || br.bitpos() > (u64)n * 8 + 64) { status = 7; break; }
+    }
+    tb->status = status; tb->end_bit = br.bitpos(); tb->nsym = nsym; tb->ngroups = g;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// symbols: one thread per 50-symbol group
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dec_syms(const u8 *in, size_t n, const u8 *sel_all, u32 sel_stride,
+                                                  const DecTables *tabs, const u32 *gbit_all, u16 *sym_all, u32 sym_stride) {
+    u32 b = blockIdx.y;
+    const DecTables *tb = tabs + b;
+    if (tb->status) return;
+    const u32 ng = tb->ngroups;
+    if (blockIdx.x * 128 >= ng) return;
+    __shared__ SmemTables st;
+    load_tables(st, tb);
+    __syncthreads();
+    u32 g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= ng) return;
+    const int alpha = (int)tb->alpha;
+    const int t = sel_all[(size_t)b * sel_stride + g];
+    BitBuf br;
+    br.init(in, n, tb->data_bit + gbit_all[(size_t)b * sel_stride + g]);
+    u16 *so = sym_all + (size_t)b * sym_stride + (size_t)g * 50;
+    u32 left = tb->nsym - g * 50;
+    int cnt = (int)min(50u, left);
+    for (int k = 0; k < cnt; k++) {
+        int s = decode_one(br, st, t, alpha);
+        so[k] = (u16)(s < 0 ? alpha - 1 : s);                  // k_dec_bounds already validated every code
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// inverse MTF + RUNA/RUNB (rle2_mtf.rs:191-287) by chunks
+// ---------------------------------------------------------------------------------------------------------
+// chunk c covers symbols [cut(c), cut(c+1)): cut(0) = 0, cut(c) = first index >= c*DCH holding a non-run symbol
+// (a run is at most 20 symbols long), cut(nch) = nsym.
+__device__ __forceinline__ u32 chunk_cut(const u16 *sym, u32 nsym, u32 c, u32 nch) {
+    if (c == 0) return 0;
+    if (c >= nch) return nsym;
+    u32 i = c * DCH;
+    while (i < nsym && sym[i] <= 1) i++;
+    return i;
+}
+
+// WRITE = 0: permutation of the chunk (perm_out[i] = start-list position of the value that ends at position i)
+//            and the number of bytes it produces.  WRITE = 1: decode with the real start list into tt.
+template <int WRITE>
+__global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const u16 *sym_all, u32 sym_stride,
+                                                    u8 *lists, u32 *ccount, const u32 *coff, u32 ch_stride,
+                                                    u8 *tt_all, u32 stride, u32 max_block) {
+    const u32 b = blockIdx.y;
+    const DecTables *tb = tabs + b;
+    if (tb->status) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 nsym = tb->nsym;
+    const u32 nch = (nsym + DCH - 1) / DCH;
+    const u32 c = blockIdx.x * 8 + w;
+    if (c >= nch) return;
+    const u16 *sym = sym_all + (size_t)b * sym_stride;
+    const u32 eob = tb->alpha - 1;
+    u32 i = chunk_cut(sym, nsym, c, nch);
+    const u32 e = chunk_cut(sym, nsym, c + 1, nch);
+    u8 *lst = lists + ((size_t)b * ch_stride + c) * 256;
+    // MTF list across the warp: positions 0..31 one per lane, 32..255 as 7 bytes per lane (low 56 bits)
+    u32 fw; u64 tl = 0;
+    if (WRITE) {
+        fw = lst[lane];
+#pragma unroll
+        for (int k = 0; k < 7; k++) tl |= (u64)lst[32 + 7 * lane + k] << (8 * k);
+    } else {
+        fw = (u32)lane;
+#pragma unroll
+        for (int k = 0; k < 7; k++) tl |= (u64)(32 + 7 * lane + k) << (8 * k);
+    }
+    const u64 LOW7 = 0x00FFFFFFFFFFFFFFull;
+    u8 *tt = tt_all + (size_t)b * stride;
+    const u32 o_start = WRITE ? coff[(size_t)b * ch_stride + c] : 0u;
+    u32 nblk = o_start;                       // output position (WRITE) / produced bytes (count)
+    u32 runlen = 0, runbit = 1;
+    u32 stage = 0;                            // byte staged by lane (nblk & 31)
+    bool bad = false;
+    // a pending run repeats the list front: finish the partially staged 32-byte line, whole lines, stage the rest
+#define FLUSH_RUN()                                                                                     \
+    do {                                                                                                \
+        if (WRITE) {                                                                                    \
+            u32 cv = __shfl_sync(0xffffffffu, fw, 0);                                                   \
+            u32 head = min(runlen, (32u - (nblk & 31u)) & 31u);                                         \
+            if (head) {                                                                                 \
+                u32 slot = nblk & 31u;                                                                  \
+                if ((u32)lane >= slot && (u32)lane < slot + head) stage = cv;                           \
+                nblk += head; runlen -= head;                                                           \
+                if ((nblk & 31u) == 0 && nblk - 32 + lane >= o_start) tt[nblk - 32 + lane] = (u8)stage; \
+            }                                                                                           \
+            while (runlen >= 32) { tt[nblk + lane] = (u8)cv; nblk += 32; runlen -= 32; }                \
+            if (runlen) { if ((u32)lane < runlen) stage = cv; nblk += runlen; }                         \
+        } else nblk += runlen;                                                                          \
+        runlen = 0;                                                                                     \
+    } while (0)
+    for (u32 i0 = i; i0 < e && !bad; i0 += 32) {
+        const int cnt = (int)min(32u, e - i0);
+        const u32 mine = lane < cnt ? (u32)sym[i0 + lane] : 0u;
+        for (int q = 0; q < cnt; q++) {
+            const u32 s = __shfl_sync(0xffffffffu, mine, q);
+            if (s <= 1) { runlen += runbit << s; runbit <<= 1; if (runlen > max_block) { bad = true; break; } continue; }
+            if (runlen) {
+                if (nblk - o_start + runlen > max_block) { bad = true; break; }
+                FLUSH_RUN();
+            }
+            runbit = 1;
+            if (s == eob) break;
+            const u32 pos = s - 1;
+            u32 v;
+            const u32 up = __shfl_up_sync(0xffffffffu, fw, 1);
+            if (pos < 32) {
+                v = __shfl_sync(0xffffffffu, fw, (int)pos);
+                if ((u32)lane <= pos) fw = lane ? up : v;
+            } else {
+                int Lh = (int)((pos - 32) / 7), kb = (int)((pos - 32) % 7);
+                u32 mb = (u32)(tl >> (8 * kb)) & 0xffu;
+                v = __shfl_sync(0xffffffffu, mb, Lh);
+                u32 carry = __shfl_sync(0xffffffffu, fw, 31);
+                u32 top = (u32)(tl >> 48) & 0xffu;
+                u32 incoming = __shfl_up_sync(0xffffffffu, top, 1);
+                if (lane == 0) incoming = carry;
+                if (lane < Lh) tl = ((tl << 8) | incoming) & LOW7;
+                else if (lane == Lh) {
+                    u64 lowmask = kb ? ((1ull << (8 * kb)) - 1) : 0ull;
+                    u64 keepmask = (~((1ull << (8 * (kb + 1))) - 1)) & LOW7;
+                    tl = (tl & keepmask) | (((tl & lowmask) << 8) | incoming);
+                }
+                fw = lane ? up : v;
+            }
+            if (WRITE) {
+                if ((nblk & 31u) == (u32)lane) stage = v;
+                nblk++;
+                if ((nblk & 31u) == 0 && nblk - 32 + lane >= o_start) tt[nblk - 32 + lane] = (u8)stage;
+            } else nblk++;
+            if (nblk - o_start > max_block) { bad = true; break; }
+        }
+    }
+    if (runlen && !bad) {                     // the run that ends exactly at the cut
+        if (nblk - o_start + runlen > max_block) bad = true;
+        else FLUSH_RUN();
+    }
+#undef FLUSH_RUN
+    if (WRITE) {
+        u32 lb = nblk & ~31u;
+        if ((nblk & 31u) && (u32)lane < (nblk & 31u) && lb + lane >= o_start) tt[lb + lane] = (u8)stage;
+    } else {
+        lst[lane] = (u8)fw;
+#pragma unroll
+        for (int k = 0; k < 7; k++) lst[32 + 7 * lane + k] = (u8)(tl >> (8 * k));
+        if (lane == 0) ccount[(size_t)b * ch_stride + c] = bad ? 0xFFFFFFFFu : nblk;
+    }
+}
+
+// one CTA per block: lists[c] := MTF list at the start of chunk c (it holds chunk c's permutation on entry),
+// coff[c] = output offset of chunk c, nblock = total
+__global__ void __launch_bounds__(256) k_dec_chunk_scan(DecTables *tabs, u8 *lists, const u32 *ccount, u32 *coff,
+                                                        u32 ch_stride, u32 max_block) {
+    const u32 b = blockIdx.x;
+    DecTables *tb = tabs + b;
+    if (tb->status) return;
+    const u32 nch = (tb->nsym + DCH - 1) / DCH;
+    __shared__ u8 cur[2][256];
+    const int i = threadIdx.x;
+    cur[0][i] = tb->seq[i];
+    __syncthreads();
+    u8 *L = lists + (size_t)b * ch_stride * 256;
+    int ph = 0;
+    u32 pnext = nch ? L[i] : 0;
+    for (u32 c = 0; c < nch; c++) {
+        u32 p = pnext;                                           // position (in the start list) of what ends at i
+        if (c + 1 < nch) pnext = L[(size_t)(c + 1) * 256 + i];   // next permutation is independent of the state
+        u8 mine = cur[ph][i];
+        L[(size_t)c * 256 + i] = mine;                           // start list of chunk c
+        cur[ph ^ 1][i] = cur[ph][p];
+        __syncthreads();
+        ph ^= 1;
+    }
+    if (i == 0) {
+        u64 sum = 0; u32 status = 0;
+        for (u32 c = 0; c < nch; c++) {
+            u32 v = ccount[(size_t)b * ch_stride + c];
+            coff[(size_t)b * ch_stride + c] = (u32)sum;
+            if (v == 0xFFFFFFFFu) { status = 9; break; }
+            sum += v;
+            if (sum > max_block) { status = 9; break; }
+        }
+        tb->nblock = (u32)sum;
+        if (!status && (sum == 0 || tb->key >= sum)) status = 10;
+        if (status) tb->status = status;
+    }
+}

@@ -77,21 +77,31 @@ def main():
         for level in range(1, 10):
             run("sweep_mixed", data, level, eng, L, verify=(level in (1, 9)))
     if "decode" in which:
+        import ctypes as C
         data = corpus.text(100_000_000, 2)
-        stream = eng.compress(data, 9)
-        eng.decompress(stream, max_out=data.size + 1024)
+        stream = np.frombuffer(eng.compress(data, 9), dtype=np.uint8)
+        # pinned host buffers, straight through the C ABI (the ctypes convenience wrapper allocates and copies)
+        h_in = torch.from_numpy(stream.copy()).pin_memory()
+        h_out = torch.empty(data.size + 1024, dtype=torch.uint8).pin_memory()
+        n_out = C.c_size_t()
+
+        def dec():
+            rc = L.bz2b200_decompress_stream(eng._h, h_in.data_ptr(), stream.size, h_out.data_ptr(), h_out.numel(), C.byref(n_out))
+            assert rc == 0, rc
+        dec()
         best = 1e9
         for _ in range(3):
             t0 = time.perf_counter()
-            out = eng.decompress(stream, max_out=data.size + 1024)
+            dec()
             best = min(best, time.perf_counter() - t0)
         eng.set_timing(2)
         eng.reset_kernel_stats()
-        eng.decompress(stream, max_out=data.size + 1024)
+        dec()
         ks = {k: round(v[0], 3) for k, v in sorted(eng.kernel_stats().items(), key=lambda kv: -kv[1][0])}
+        ok = n_out.value == data.size and bool((h_out[:data.size].numpy() == data).all())
         print(json.dumps({"config": "decode_text100m", "MBps_output": data.size / 1e6 / best, "ms": best * 1e3,
-                          "ok": out == data.tobytes(), "kernel_ms": ks,
-                          "note": "host buffers (H2D of .bz2 and D2H of the text included)"}),
+                          "ok": ok, "kernel_ms": ks, "kernel_ms_sum": round(sum(ks.values()), 3),
+                          "note": "pinned host buffers (H2D of .bz2 and D2H of the text included)"}),
               flush=True)
 
 
