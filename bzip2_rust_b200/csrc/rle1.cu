@@ -309,119 +309,147 @@ __device__ __forceinline__ u32 exit_cursor(u32 g, long long R) {
     return (R & 1) ? g + (u32)R : g + (u32)R + 1;
 }
 
-__global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
-    // all 32 lanes run the same control flow (every value is warp-uniform); lane 0 writes the results
-    const bool writer = threadIdx.x == 0;
+// One block of the chain: the block that starts at input position s.  COOP = true: called by all lanes with the
+// same s (the binary search over OUT is warp cooperative); COOP = false would let a lane plan on its own.
+enum { PLAN_OK = 0, PLAN_STOP = 1, PLAN_SEARCH = 2 };
+template <bool COOP>
+__device__ __forceinline__ int plan_block(const ChainArgs &a, u32 s, BlockRec &r) {
     const u32 W = a.W, B = a.B;
-    u32 s = a.s0, nb = 0;                                       // s0: a true block start inside the scanned window
     const u32 margin = a.is_eof ? 0u : 1024u;
-    while (s < W && s < a.stop_at && nb < a.max_blocks) {
-        BlockRec r;
-        r.s = s; r.last = 0;
-        // ---- first run, parsed from s ----
-        u32 re = run_end_from(a.RS, W, s);
-        if (!a.is_eof && re + margin > W) break;                // run may continue past the window
-        u32 Lc = re - s;
-        u32 nfull = Lc / 255u, rem = Lc % 255u;
-        u32 ng_avail = nfull + (rem >= 4 ? 1u : 0u);
-        u32 jmax = (B - 1 + 4) / 5;                             // groups j with 5j + 1 < B
-        u32 g, out_g;
-        bool done = false;
-        u32 e = 0;
-        if (ng_avail > jmax) {                                  // the size limit falls inside the first run
-            g = s + 255u * jmax; out_g = 5u * jmax;
-            e = g + 1;
-            r.re = re; r.out_re = 0;                            // unused: block ends before re
-            done = true;
-        } else {
-            g = s + 255u * nfull + (rem >= 4 ? rem : 0u);
-            out_g = 5u * ng_avail;
-            r.re = re; r.out_re = out_g + (re - g);
+    r.s = s; r.last = 0;
+    // ---- first run, parsed from s ----
+    u32 re = run_end_from(a.RS, W, s);
+    if (!a.is_eof && re + margin > W) return PLAN_STOP;         // run may continue past the window
+    u32 Lc = re - s;
+    u32 nfull = Lc / 255u, rem = Lc % 255u;
+    u32 ng_avail = nfull + (rem >= 4 ? 1u : 0u);
+    u32 jmax = (B - 1 + 4) / 5;                                 // groups j with 5j + 1 < B
+    u32 g, out_g;
+    bool done = false;
+    u32 e = 0;
+    if (ng_avail > jmax) {                                      // the size limit falls inside the first run
+        g = s + 255u * jmax; out_g = 5u * jmax;
+        e = g + 1;
+        r.re = re; r.out_re = 0;                                // unused: block ends before re
+        done = true;
+    } else {
+        g = s + 255u * nfull + (rem >= 4 ? rem : 0u);
+        out_g = 5u * ng_avail;
+        r.re = re; r.out_re = out_g + (re - g);
+    }
+    bool has_group_after_off = ng_avail > 0 && g > a.off_from;
+    if (!done) {
+        // OUTs(x) = OUT[x] + off for x >= re
+        long long off = (long long)r.out_re - (long long)a.OUT[re];
+        long long target = (long long)B - 1 - off;              // first x >= re with OUT[x] >= target
+        u32 x1;
+        if ((long long)a.OUT[W] < target) x1 = W + 1;           // never reached inside the window
+        else {
+            // run-free data emits one byte per input byte, so the answer is usually re + (bytes still to emit):
+            // verify that guess with two independent loads before falling back to the search
+            long long need = target - (long long)a.OUT[re];
+            u64 guess = (u64)re + (u64)(need > 0 ? need : 0);
+            if (need <= 0) x1 = re;
+            else if (guess <= W && (long long)a.OUT[guess] >= target && (long long)a.OUT[guess - 1] < target) x1 = (u32)guess;
+            else if (COOP) x1 = warp_lower_bound(a.OUT, re, W, target);
+            else return PLAN_SEARCH;
         }
-        bool has_group_after_off = ng_avail > 0 && g > a.off_from;
-        if (!done) {
-            // OUTs(x) = OUT[x] + off for x >= re
-            long long off = (long long)r.out_re - (long long)a.OUT[re];
-            long long target = (long long)B - 1 - off;          // first x >= re with OUT[x] >= target
-            u32 x1;
-            if ((long long)a.OUT[W] < target) x1 = W + 1;       // never reached inside the window
-            else {
-                // run-free data emits one byte per input byte, so the answer is usually re + (bytes still to emit):
-                // verify that guess with two independent loads before falling back to the search
-                long long need = target - (long long)a.OUT[re];
-                u64 guess = (u64)re + (u64)(need > 0 ? need : 0);
-                if (need <= 0) x1 = re;
-                else if (guess <= W && (long long)a.OUT[guess] >= target && (long long)a.OUT[guess - 1] < target) x1 = (u32)guess;
-                else x1 = warp_lower_bound(a.OUT, re, W, target);
-            }
-            u32 gl = NOQ;                                       // start of the last taken global group
-            if (x1 <= W) {
-                // the only group that can sit exactly at the limit starts in [x1, x1+3]
-                u32 hiq = min(x1 + 3, W - 1);
-                if (x1 < W) {
-                    u32 q1 = a.LASTQ[hiq];
-                    if (q1 != NOQ && q1 >= x1 && q1 >= re && (long long)a.OUT[q1] + off == (long long)B - 1) {
-                        // taken iff it is seen at cursor q1 itself: (q1 - previous group end) odd
-                        u32 gp = g;
-                        if (q1 > 0) {
-                            u32 qp = a.LASTQ[q1 - 1];
-                            if (qp != NOQ && qp >= re) gp = group_end(a.x, W, qp);
-                        }
-                        if (((q1 - gp) & 1u) == 1u) gl = q1;
+        u32 gl = NOQ;                                           // start of the last taken global group
+        if (x1 <= W) {
+            // the only group that can sit exactly at the limit starts in [x1, x1+3]
+            u32 hiq = min(x1 + 3, W - 1);
+            if (x1 < W) {
+                u32 q1 = a.LASTQ[hiq];
+                if (q1 != NOQ && q1 >= x1 && q1 >= re && (long long)a.OUT[q1] + off == (long long)B - 1) {
+                    // taken iff it is seen at cursor q1 itself: (q1 - previous group end) odd
+                    u32 gp = g;
+                    if (q1 > 0) {
+                        u32 qp = a.LASTQ[q1 - 1];
+                        if (qp != NOQ && qp >= re) gp = group_end(a.x, W, qp);
                     }
+                    if (((q1 - gp) & 1u) == 1u) gl = q1;
                 }
-                if (gl == NOQ && x1 > re) {
-                    u32 qp = a.LASTQ[x1 - 1];
-                    if (qp != NOQ && qp >= re) gl = qp;
-                }
-            } else if (W > re) {
-                u32 qp = a.LASTQ[W - 1];
+            }
+            if (gl == NOQ && x1 > re) {
+                u32 qp = a.LASTQ[x1 - 1];
                 if (qp != NOQ && qp >= re) gl = qp;
             }
-            if (gl != NOQ) {
-                g = group_end(a.x, W, gl);
-                out_g = (u32)((long long)a.OUT[gl] + off + 5);
-                if (gl >= a.off_from) has_group_after_off = true;
-            } else {
-                // no global group taken: the literal stretch continues from the first run's last group
-                // (g, out_g unchanged)
-            }
-            long long R = (long long)B - (long long)out_g;
-            e = exit_cursor(g, R);
+        } else if (W > re) {
+            u32 qp = a.LASTQ[W - 1];
+            if (qp != NOQ && qp >= re) gl = qp;
         }
-        // ---- window / EOF handling ----
-        if (a.is_eof) {
-            u32 lim = has_group_after_off ? W - 1 : W - 2;      // size exit only at a cursor visited before the EOF arms
-            if (W < 2 || e > lim || e > W) {                     // final block takes everything (rle1.rs:115-139)
-                e = W; r.last = 1;
-                if (!done) {
-                    // every group up to the end is taken
-                    if (W > re) {
-                        u32 qp = a.LASTQ[W - 1];
-                        if (qp != NOQ && qp >= re) {
-                            long long off = (long long)r.out_re - (long long)a.OUT[re];
-                            g = group_end(a.x, W, qp);
-                            out_g = (u32)((long long)a.OUT[qp] + off + 5);
-                        }
-                    }
-                } else {
-                    // limit fell inside the first run but the file ends here: recompute as "all groups taken"
-                    g = s + 255u * nfull + (rem >= 4 ? rem : 0u);
-                    out_g = 5u * ng_avail;
-                    r.out_re = out_g + (re - g);
-                }
-            }
-        } else if (e + margin > W) {
-            break;                                              // needs bytes beyond this window
+        if (gl != NOQ) {
+            g = group_end(a.x, W, gl);
+            out_g = (u32)((long long)a.OUT[gl] + off + 5);
+            if (gl >= a.off_from) has_group_after_off = true;
         }
-        r.e = e; r.g_last = g; r.out_g = out_g;
-        r.out_len = out_g + (e - g);
-        if (r.out_len > a.max_out) break;                       // cannot happen for level <= 9; guards the batch stride
-        if (writer) a.rec[nb] = r;
-        nb++;
-        s = e;
+        // else: no global group taken, the literal stretch continues from the first run's last group
+        long long R = (long long)B - (long long)out_g;
+        e = exit_cursor(g, R);
     }
-    if (writer) { *a.nrec = nb; *a.consumed = s; }
+    // ---- window / EOF handling ----
+    if (a.is_eof) {
+        u32 lim = has_group_after_off ? W - 1 : W - 2;          // size exit only at a cursor visited before the EOF arms
+        if (W < 2 || e > lim || e > W) {                         // final block takes everything (rle1.rs:115-139)
+            e = W; r.last = 1;
+            if (!done) {
+                // every group up to the end is taken
+                if (W > re) {
+                    u32 qp = a.LASTQ[W - 1];
+                    if (qp != NOQ && qp >= re) {
+                        long long off = (long long)r.out_re - (long long)a.OUT[re];
+                        g = group_end(a.x, W, qp);
+                        out_g = (u32)((long long)a.OUT[qp] + off + 5);
+                    }
+                }
+            } else {
+                // limit fell inside the first run but the file ends here: recompute as "all groups taken"
+                g = s + 255u * nfull + (rem >= 4 ? rem : 0u);
+                out_g = 5u * ng_avail;
+                r.out_re = out_g + (re - g);
+            }
+        }
+    } else if (e + margin > W) {
+        return PLAN_STOP;                                       // needs bytes beyond this window
+    }
+    r.e = e; r.g_last = g; r.out_g = out_g;
+    r.out_len = out_g + (e - g);
+    if (r.out_len > a.max_out) return PLAN_STOP;                // cannot happen for level <= 9; guards the batch stride
+    return PLAN_OK;
+}
+
+// The chain s_{k+1} = e(s_k) is sequential and a block costs ~7 dependent loads from arrays far larger than the L2
+// (~6 us of DRAM latency per block).  The next block starts within a few hundred bytes of s + (span of this block),
+// so while lane-uniform code plans block k the lanes prefetch that neighbourhood of RS / OUT / LASTQ / x for block
+// k+1 (its start, and its end one span further).  (Planning 32 guessed starts at once was tried: real text has a
+// few runs per block, spans differ by some bytes, and only lane 0's guess is ever confirmed.)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
+    // all 32 lanes run the same control flow (every value is warp-uniform); lane 0 writes the results
+    const int lane = threadIdx.x;
+    const u32 W = a.W;
+    u32 s = a.s0, nb = 0;                                       // s0: a true block start inside the scanned window
+    u32 span = a.B;
+    while (s < W && s < a.stop_at && nb < a.max_blocks) {
+        {   // lanes 0..15: around the next block's start; lanes 16..31: around its end.  128-byte lines of u32 = 32 entries.
+            u64 c = (u64)s + (u64)span * (lane < 16 ? 1u : 2u);
+            long long p = (long long)c - 1024 + (long long)(lane & 15) * 128;       // 2 KB window of positions
+            if (p >= 0 && (u64)p + 32 < (u64)W) {
+                prefetch_l2(a.OUT + p); prefetch_l2(a.OUT + p + 32); prefetch_l2(a.OUT + p + 64); prefetch_l2(a.OUT + p + 96);
+                prefetch_l2(a.LASTQ + p); prefetch_l2(a.LASTQ + p + 32); prefetch_l2(a.LASTQ + p + 64); prefetch_l2(a.LASTQ + p + 96);
+                prefetch_l2(a.RS + p); prefetch_l2(a.RS + p + 32); prefetch_l2(a.RS + p + 64); prefetch_l2(a.RS + p + 96);
+                prefetch_l2(a.x + p);
+            }
+        }
+        BlockRec r;
+        if (plan_block<true>(a, s, r) != PLAN_OK) break;
+        if (lane == 0) a.rec[nb] = r;
+        nb++;
+        span = r.e - s;
+        s = r.e;
+    }
+    if (lane == 0) { *a.nrec = nb; *a.consumed = s; }
 }
 
 // ---------------------------------------------------------------------------------------
