@@ -1,8 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/kernel_times.py 1000 text 9 1 > gpurun_out/kt9_1g.json 2>gpurun_out/kt9.err
-python - <<'PY'
-import json
-r=json.loads(open('gpurun_out/kt9_1g.json').read())
-print(r['corpus'], r['mb'], r['wall_ms_untimed_mode'], r['stage_ms'], r.get('libbz2_roundtrip'), r['z'])
-PY
-python tools/run_configs.py decode 2>&1 | tail -1 | cut -c1-800
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench6.json 2> gpurun_out/bench6.err; cut -c1-700 gpurun_out/bench6.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_v3.csv python bench.py --steps 1 --warmup 3 --no-verify > gpurun_out/ncu_l.log 2>&1
+wc -l gpurun_out/r01_launches_v3.csv
