@@ -351,15 +351,25 @@ __device__ __forceinline__ int plan_block(const ChainArgs &a, u32 s, BlockRec &r
             u64 guess = (u64)re + (u64)(need > 0 ? need : 0);
             if (need <= 0) x1 = re;
             else if (guess <= W && (long long)a.OUT[guess] >= target && (long long)a.OUT[guess - 1] < target) x1 = (u32)guess;
-            else if (COOP) x1 = warp_lower_bound(a.OUT, re, W, target);
-            else return PLAN_SEARCH;
+            else if (COOP) {
+                // a few runs per block move the answer some bytes away from the guess: search +-512 positions first
+                // (two probe rounds, and that neighbourhood was prefetched) before the whole window (five rounds)
+                u64 g64 = guess > W ? W : guess;
+                u32 lo_w = g64 > (u64)re + 512 ? (u32)g64 - 512u : re;
+                u32 hi_w = g64 + 512 < (u64)W ? (u32)g64 + 512u : W;
+                if ((long long)a.OUT[lo_w] < target && (long long)a.OUT[hi_w] >= target) x1 = warp_lower_bound(a.OUT, lo_w, hi_w, target);
+                else x1 = warp_lower_bound(a.OUT, re, W, target);
+            } else return PLAN_SEARCH;
         }
         u32 gl = NOQ;                                           // start of the last taken global group
         if (x1 <= W) {
             // the only group that can sit exactly at the limit starts in [x1, x1+3]
             u32 hiq = min(x1 + 3, W - 1);
+            // both look-ups depend only on x1: issue them together (each is a DRAM/L2 round trip on the serial chain)
+            u32 q1_pre = x1 < W ? a.LASTQ[hiq] : NOQ;
+            u32 qp_pre = x1 > re ? a.LASTQ[x1 - 1] : NOQ;
             if (x1 < W) {
-                u32 q1 = a.LASTQ[hiq];
+                u32 q1 = q1_pre;
                 if (q1 != NOQ && q1 >= x1 && q1 >= re && (long long)a.OUT[q1] + off == (long long)B - 1) {
                     // taken iff it is seen at cursor q1 itself: (q1 - previous group end) odd
                     u32 gp = g;
@@ -371,7 +381,7 @@ __device__ __forceinline__ int plan_block(const ChainArgs &a, u32 s, BlockRec &r
                 }
             }
             if (gl == NOQ && x1 > re) {
-                u32 qp = a.LASTQ[x1 - 1];
+                u32 qp = qp_pre;
                 if (qp != NOQ && qp >= re) gl = qp;
             }
         } else if (W > re) {
@@ -379,8 +389,9 @@ __device__ __forceinline__ int plan_block(const ChainArgs &a, u32 s, BlockRec &r
             if (qp != NOQ && qp >= re) gl = qp;
         }
         if (gl != NOQ) {
+            u32 out_gl = a.OUT[gl];                             // independent of the group_end walk below
             g = group_end(a.x, W, gl);
-            out_g = (u32)((long long)a.OUT[gl] + off + 5);
+            out_g = (u32)((long long)out_gl + off + 5);
             if (gl >= a.off_from) has_group_after_off = true;
         }
         // else: no global group taken, the literal stretch continues from the first run's last group
