@@ -370,6 +370,8 @@ __device__ __forceinline__ u32 chunk_cut(const u16 *sym, u32 nsym, u32 c, u32 nc
     return i;
 }
 
+__device__ __forceinline__ bool below_start(u32 pos, u32 start) { return pos < start; }   // start is 0 in count mode
+
 // WRITE = 0: permutation of the chunk (perm_out[i] = start-list position of the value that ends at position i)
 //            and the number of bytes it produces.  WRITE = 1: decode with the real start list into tt.
 template <int WRITE>
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const
                 u32 slot = nblk & 31u;                                                                  \
                 if ((u32)lane >= slot && (u32)lane < slot + head) stage = cv;                           \
                 nblk += head; runlen -= head;                                                           \
-                if ((nblk & 31u) == 0 && nblk - 32 + lane >= o_start) tt[nblk - 32 + lane] = (u8)stage; \
+                if ((nblk & 31u) == 0 && !below_start(nblk - 32 + lane, o_start)) tt[nblk - 32 + lane] = (u8)stage; \
             }                                                                                           \
             while (runlen >= 32) { tt[nblk + lane] = (u8)cv; nblk += 32; runlen -= 32; }                \
             if (runlen) { if ((u32)lane < runlen) stage = cv; nblk += runlen; }                         \
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const
             if (WRITE) {
                 if ((nblk & 31u) == (u32)lane) stage = v;
                 nblk++;
-                if ((nblk & 31u) == 0 && nblk - 32 + lane >= o_start) tt[nblk - 32 + lane] = (u8)stage;
+                if ((nblk & 31u) == 0 && !below_start(nblk - 32 + lane, o_start)) tt[nblk - 32 + lane] = (u8)stage;
             } else nblk++;
             if (nblk - o_start > max_block) { bad = true; break; }
         }
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const
 #undef FLUSH_RUN
     if (WRITE) {
         u32 lb = nblk & ~31u;
-        if ((nblk & 31u) && (u32)lane < (nblk & 31u) && lb + lane >= o_start) tt[lb + lane] = (u8)stage;
+        if ((nblk & 31u) && (u32)lane < (nblk & 31u) && !below_start(lb + lane, o_start)) tt[lb + lane] = (u8)stage;
     } else {
         lst[lane] = (u8)fw;
 #pragma unroll

@@ -493,15 +493,13 @@ __global__ void __launch_bounds__(BZ_THREADS) k_rle_emit(const u8 *x, u32 W, con
                     o[0] = c; o[1] = c; o[2] = c; o[3] = c; o[4] = (u8)(cl - 4);
                 }
             } else out[5u * j + (i - cs)] = c;
-        } else {                                                // global parse
-            u32 rs = RS[i];
-            u32 cs = rs + ((i - rs) / 255u) * 255u;
-            bool grp = group_start_at(x, W, cs, rs);
-            u32 o = (u32)((long long)OUT[i] + off);
-            if (!grp) out[o] = c;
-            else if (i == cs) {
-                u32 ge = group_end(x, W, cs);
-                out[o] = c; out[o + 1] = c; out[o + 2] = c; out[o + 3] = c; out[o + 4] = (u8)(ge - cs - 4);
+        } else {                                                // global parse: OUT[i+1] - OUT[i] = bytes emitted at i
+            u32 o0 = OUT[i], o1 = OUT[i + 1];
+            u32 o = (u32)((long long)o0 + off);
+            if (o1 - o0 == 1u) out[o] = c;                      // literal
+            else if (o1 != o0) {                                // group start (5 bytes); the rest of a group emits nothing
+                u32 ge = group_end(x, W, i);
+                out[o] = c; out[o + 1] = c; out[o + 2] = c; out[o + 3] = c; out[o + 4] = (u8)(ge - i - 4);
             }
         }
     }

@@ -1,4 +1,4 @@
-python -m pytest tests/test_stream_gpu.py tests/test_shard_gpu.py tests/test_golden.py -x -q 2>&1 | tail -2
-for c in "100 text" "256 rep" "256 mixed"; do python tools/kernel_times.py $c 9 1 2>/dev/null | python -c "
+python -m pytest tests/test_stream_gpu.py tests/test_golden.py -x -q 2>&1 | tail -2
+for c in "100 text" "128 rep"; do python tools/kernel_times.py $c 9 1 2>/dev/null | python -c "
 import sys,json
-r=json.loads(sys.stdin.read()); print(r['corpus'], r['adler'], r['stage_ms']['rle1_crc_split'], r.get('libbz2_roundtrip'), [k for k in r['kernels'] if 'chain' in k[0]])"; done
+r=json.loads(sys.stdin.read()); print(r['corpus'], r['adler'], r['stage_ms']['rle1_crc_split'], r.get('libbz2_roundtrip'), [k for k in r['kernels'] if 'rle' in k[0]])"; done
