@@ -239,13 +239,6 @@ __global__ void __launch_bounds__(BZ_THREADS) k_rle_scan(ScanArgs a) {
 #undef XB
 }
 
-__device__ __forceinline__ bool group_start_at(const u8 *x, u32 W, u32 i, u32 rs) {
-    if ((i - rs) % 255u != 0) return false;
-    if (i + 3 >= W) return false;
-    u8 c = x[i];
-    return x[i + 1] == c && x[i + 2] == c && x[i + 3] == c;
-}
-
 // ---------------------------------------------------------------------------------------
 // the block chain (one warp; lane 0 carries the logic)
 // ---------------------------------------------------------------------------------------
