@@ -224,6 +224,18 @@ def _main(args, real_stdout):
         shm = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(h_out.numel(),))
         shm[:] = 0                                             # touch the pages once, outside the timed region
         t_shm = torch.from_numpy(shm)
+        # block-chain hand-off between neighbouring ranks: a mailbox in shared host memory, slot r = (sequence number,
+        # first block start of rank r).  One boundary per step and neighbour; an NCCL send/recv pair cost ~0.4 ms per hop
+        # (launch + stream sync), and the hops are serial.  BENCH_CHAIN=nccl keeps the old path.
+        box_path = shm_path + ".chain"
+        if rank == 0:
+            with open(box_path, "wb") as f:
+                f.truncate(16 * (world + 1))
+        dist.barrier()
+        box = np.memmap(box_path, dtype=np.int64, mode="r+", shape=(world + 1, 2))
+        if rank == 0:
+            box[:] = 0
+        dist.barrier()
         # page-lock the shared mapping so that every rank's D2H lands in it directly (no staging copy)
         shm_pinned = int(torch.cuda.cudart().cudaHostRegister(t_shm.data_ptr(), t_shm.numel(), 0)) == 0
 
@@ -236,17 +248,33 @@ def _main(args, real_stdout):
     out_len = C.c_size_t()
     state = {}
 
+    use_nccl_chain = os.environ.get("BENCH_CHAIN", "shm") == "nccl"
+    state["seq"] = 0
+
     def chain_recv():
+        """-> first block start of this rank (the previous rank's last block end)."""
+        state["seq"] += 1
         if rank == 0:
             return 0
-        t = torch.zeros(1, dtype=torch.int64, device=dev)
-        dist.recv(t, rank - 1)
-        return int(t.item())
+        if use_nccl_chain:
+            t = torch.zeros(1, dtype=torch.int64, device=dev)
+            dist.recv(t, rank - 1)
+            return int(t.item())
+        seq = state["seq"]
+        deadline = time.perf_counter() + 60.0
+        while int(box[rank, 0]) != seq:                        # written last by the sender, after the value
+            if time.perf_counter() > deadline:
+                raise RuntimeError("chain hand-off timed out on rank %d" % rank)
+        return int(box[rank, 1])
 
     def chain_send(nxt):
         if rank < world - 1:
-            state["chain_t"] = torch.tensor([nxt], dtype=torch.int64, device=dev)      # keep alive until sent
-            dist.send(state["chain_t"], rank + 1)
+            if use_nccl_chain:
+                state["chain_t"] = torch.tensor([nxt], dtype=torch.int64, device=dev)      # keep alive until sent
+                dist.send(state["chain_t"], rank + 1)
+                return
+            box[rank + 1, 1] = nxt
+            box[rank + 1, 0] = state["seq"]                    # x86 keeps the two stores in order
 
     def step_dev():
         """HBM-resident.  N > 1: scan own slice, take the chain from rank-1, pass it on, compress own blocks."""
@@ -487,10 +515,11 @@ def _main(args, real_stdout):
     }
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
-        try:
-            os.unlink(shm_path)
-        except OSError:
-            pass
+        for pth in (shm_path, shm_path + ".chain"):
+            try:
+                os.unlink(pth)
+            except OSError:
+                pass
         dist.destroy_process_group()
     return 0
 
