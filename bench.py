@@ -225,14 +225,14 @@ def _main(args, real_stdout):
         shm[:] = 0                                             # touch the pages once, outside the timed region
         t_shm = torch.from_numpy(shm)
         # block-chain hand-off between neighbouring ranks: a mailbox in shared host memory, slot r = (sequence number,
-        # first block start of rank r).  One boundary per step and neighbour; an NCCL send/recv pair cost ~0.4 ms per hop
+        # first block start of rank r, sequence number the receiver has consumed).  One boundary per step and neighbour; an NCCL send/recv pair cost ~0.4 ms per hop
         # (launch + stream sync), and the hops are serial.  BENCH_CHAIN=nccl keeps the old path.
         box_path = shm_path + ".chain"
         if rank == 0:
             with open(box_path, "wb") as f:
-                f.truncate(16 * (world + 1))
+                f.truncate(24 * (world + 1))
         dist.barrier()
-        box = np.memmap(box_path, dtype=np.int64, mode="r+", shape=(world + 1, 2))
+        box = np.memmap(box_path, dtype=np.int64, mode="r+", shape=(world + 1, 3))    # seq, value, ack
         if rank == 0:
             box[:] = 0
         dist.barrier()
@@ -265,7 +265,9 @@ def _main(args, real_stdout):
         while int(box[rank, 0]) != seq:                        # written last by the sender, after the value
             if time.perf_counter() > deadline:
                 raise RuntimeError("chain hand-off timed out on rank %d" % rank)
-        return int(box[rank, 1])
+        v = int(box[rank, 1])
+        box[rank, 2] = seq                                     # the slot may be reused
+        return v
 
     def chain_send(nxt):
         if rank < world - 1:
@@ -273,6 +275,10 @@ def _main(args, real_stdout):
                 state["chain_t"] = torch.tensor([nxt], dtype=torch.int64, device=dev)      # keep alive until sent
                 dist.send(state["chain_t"], rank + 1)
                 return
+            deadline = time.perf_counter() + 60.0
+            while int(box[rank + 1, 2]) != state["seq"] - 1:   # the receiver has not read the previous step's value yet
+                if time.perf_counter() > deadline:
+                    raise RuntimeError("chain hand-off: rank %d never acknowledged" % (rank + 1))
             box[rank + 1, 1] = nxt
             box[rank + 1, 0] = state["seq"]                    # x86 keeps the two stores in order
 
@@ -510,6 +516,11 @@ def _main(args, real_stdout):
         "stage_ms": stage,
         "top_kernels": [{"kernel": k, "ms": v[0] / args.steps, "launches": v[1] // args.steps,
                          "GBps_algorithmic": (v[2] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else 0.0} for k, v in top],
+        # every kernel of the timed region: ms per step, launches per step, algorithmic GB/s and its fraction of the HBM peak
+        "kernels": [[k, round(v[0] / args.steps, 4), v[1] // args.steps,
+                     round((v[2] / 1e9) / (v[0] * 1e-3), 1) if v[0] > 0 else 0.0,
+                     round((v[2] / 1e9) / (v[0] * 1e-3) / peak, 4) if v[0] > 0 else 0.0]
+                    for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][0])],
         "verified_roundtrip_libbz2": verified,
         "compressed_bytes": int(clen),
     }
