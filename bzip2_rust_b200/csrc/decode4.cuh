@@ -62,12 +62,14 @@ struct BitBuf {
 // Bit reader over 4-byte aligned words with the next word already in flight (the walk of k_dec_bounds is one
 // long dependent chain: a load issued when it is needed would add its latency to every sixth symbol).
 struct WordBits {
-    const u32 *w; size_t nw, idx;            // idx = next word to fetch into `ahead`
+    const u32 *w; u32 last, idx;             // idx = next word to fetch into `ahead`; last = index of the last word
     u64 buf; int nb; u32 ahead;
-    __device__ __forceinline__ u32 fetch(size_t i) const { return i < nw ? __byte_perm(__ldg(w + i), 0, 0x0123) : 0u; }
-    __device__ void init(const u8 *in, size_t len, u64 bitpos) {     // `in` is 4-byte aligned, len padded reads are safe
-        w = (const u32 *)in; nw = (len + 3) / 4;
-        size_t first = (size_t)(bitpos >> 5);
+    __device__ __forceinline__ u32 fetch(u32 i) const { return __byte_perm(__ldg(w + min(i, last)), 0, 0x0123); }
+    __device__ void init(const u8 *in, size_t len, u64 bitpos) {     // `in` is 4-byte aligned, streams are < 4 GiB
+        w = (const u32 *)in; last = (u32)((len + 3) / 4) - 1u;
+        asm volatile("" : "+l"(w));          // keep the pointer in a register: ptxas otherwise re-reads the kernel
+                                             // parameter from the constant bank inside the walk (21% of its stalls)
+        u32 first = (u32)(bitpos >> 5);
         buf = ((u64)fetch(first) << 32) | fetch(first + 1);
         nb = 64;
         idx = first + 3; ahead = fetch(first + 2);
@@ -78,10 +80,9 @@ struct WordBits {
         if (nb <= 32) {
             buf |= (u64)ahead << (32 - nb);
             nb += 32;
-            size_t i = idx < nw ? idx : nw - 1;                  // clamped: a corrupt stream must not walk off the buffer
-            ahead = __byte_perm(__ldg(w + i), 0, 0x0123); idx++;
-            size_t pf = idx + 48 < nw ? idx + 48 : nw - 1;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(w + pf));
+            ahead = fetch(idx);                                  // clamped: a corrupt stream cannot walk off the buffer
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(w + min(idx + 48u, last)));
+            idx++;
         }
     }
     __device__ __forceinline__ u32 peek(int k) const { return (u32)(buf >> (64 - k)); }
@@ -229,9 +230,10 @@ __device__ __forceinline__ int decode_one(R &br, const SmemTables &s, int t, int
 // ---------------------------------------------------------------------------------------------------------
 // The walk is one dependent chain per block (probe, shift, probe ...), ~150 cycles per symbol with a one-symbol
 // table.  A 12-bit window usually holds TWO codes, so the pair table below halves the chain.
-// entry: [4:0] length of both codes if two fit (else 0), [9:5] length of the first code (0 = longer than 12 bits),
-// bit 10 = the first symbol is EOB, bit 11 = the second is, bit 12 = "special" (any of: long code, EOB): the walk
-// takes one rarely-taken branch per probe, everything else is selects (a lone warp pays ~20 cycles per branch).
+// entry: [4:0] bits to skip (both codes if two fit, else the first), [6:5] codes covered (1 or 2), [11:7] length of
+// the first code alone, bit 12 = "special" (a code longer than 12 bits, or EOB among the covered codes), bit 13 =
+// the first symbol is EOB, bit 14 = the second is.  The walk's common path is probe -> shift with no selects and
+// one never-taken branch (a lone warp pays ~5 cycles per dependent instruction and ~15 per taken branch).
 constexpr int PAIRBITS = 12;
 struct BoundsSmem {
     u16 pair[6][1 << PAIRBITS];
@@ -271,11 +273,11 @@ __global__ void __launch_bounds__(32) k_dec_bounds(const u8 *in, size_t n, const
             int l1 = canon_len(tb, t, win, PAIRBITS, alpha, s1);
             u32 e = 0x1000u;
             if (l1) {
-                e = (u32)l1 << 5;
-                if (s1 == alpha - 1) e |= 0x1400u;
+                e = (u32)l1 | (1u << 5) | ((u32)l1 << 7);
+                if (s1 == alpha - 1) e |= 0x3000u;
                 else if (l1 < PAIRBITS) {
                     int l2 = canon_len(tb, t, win << l1, PAIRBITS - l1, alpha, s2);
-                    if (l2) { e |= (u32)(l1 + l2); if (s2 == alpha - 1) e |= 0x1800u; }
+                    if (l2) { e = (u32)(l1 + l2) | (2u << 5) | ((u32)l1 << 7); if (s2 == alpha - 1) e |= 0x5000u; }
                 }
             }
             st.pair[t][v] = (u16)e;
@@ -297,33 +299,36 @@ __global__ void __launch_bounds__(32) k_dec_bounds(const u8 *in, size_t n, const
         const int t = sel[g];
         gbit[g] = (u32)(br.bitpos() - data_bit);
         g++;
-        int rem = 50;
-        do {
+        int rem = 50;                                            // every decoded symbol decrements rem, nsym is settled per group
+        while (rem > 0 && !done) {
             br.refill();
-            u32 e = pt[br.peek(PAIRBITS)];
-            if (e & 0x1000u) {                                  // rare: EOB in the window, or a code longer than 12 bits
-                u32 l1 = (e >> 5) & 31u;
-                if (l1 == 0) {
-                    int l = PAIRBITS + 1;
-                    int code = (int)br.peek(l);
-                    while (l <= 20 && code > st.limit[t][l]) { l++; code = (int)br.peek(l); }
-                    int pi = l <= 20 ? code + st.base[t][l] : -1;
-                    if (pi < 0 || pi >= alpha) { status = 7; done = true; break; }
-                    br.skip(l);
-                    nsym++; rem--;
-                    if ((int)st.perm[t][pi] == alpha - 1) { done = true; break; }
-                    continue;
+            // probes run back to back while more than 32 bits are buffered: the refill (a dozen instructions) stays out
+            // of this loop -- as predicated code inside it, it was issued on every probe
+            do {
+                u32 e = pt[br.peek(PAIRBITS)];
+                if (__builtin_expect((e & 0x1000u) != 0 || rem < 2, 0)) {
+                    // rare: EOB in the window, a code longer than 12 bits, or the last symbol of the group
+                    u32 l1 = (e >> 7) & 31u;
+                    if (l1 == 0) {
+                        int l = PAIRBITS + 1;
+                        int code = (int)br.peek(l);
+                        while (l <= 20 && code > st.limit[t][l]) { l++; code = (int)br.peek(l); }
+                        int pi = l <= 20 ? code + st.base[t][l] : -1;
+                        if (pi < 0 || pi >= alpha) { status = 7; done = true; break; }
+                        br.skip(l);
+                        rem--;
+                        if ((int)st.perm[t][pi] == alpha - 1) { done = true; break; }
+                    } else if (e & 0x2000u) { br.skip((int)l1); rem--; done = true; break; }                  // the first symbol is EOB
+                    else if ((e & 0x4000u) && rem >= 2) { br.skip((int)(e & 31u)); rem -= 2; done = true; break; }   // the second one is
+                    else if (rem >= 2 && ((e >> 5) & 3u) == 2u) { br.skip((int)(e & 31u)); rem -= 2; }
+                    else { br.skip((int)l1); rem--; }            // one symbol (group end, or EOB belongs to the next group)
+                } else {
+                    br.skip((int)(e & 31u));
+                    rem -= (int)((e >> 5) & 3u);
                 }
-                if (e & 0x400u) { br.skip((int)l1); nsym++; done = true; break; }      // the first symbol is EOB
-                if (rem >= 2) { br.skip((int)(e & 31u)); nsym += 2; done = true; break; }   // the second one is
-                br.skip((int)l1); nsym++; rem--;                // EOB is the second symbol but belongs to the next group
-                continue;
-            }
-            const bool two = (e & 31u) != 0 && rem >= 2;
-            br.skip((int)(two ? (e & 31u) : (e >> 5)));
-            const int c = two ? 2 : 1;
-            nsym += c; rem -= c;
-        } while (rem > 0);
+            } while (br.nb > 32 && rem > 0);
+        }
+        nsym += (u32)(50 - rem);
         if (nsym > max_sym || br.bitpos() > (u64)n * 8 + 64) { status = 7; break; }
     }
     tb->status = status; tb->end_bit = br.bitpos(); tb->nsym = nsym; tb->ngroups = g;
