@@ -663,7 +663,7 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     BZ_CHECK(ctx->d_agg2.ensure((size_t)nb * parts_stride * 4 + 64));
     u32 xp = gf_pow_x8(PIECE), xp256 = gf_pow_x8((u64)PIECE * 256);
     dim3 gc(parts_stride, nb);
-    ctx->prof_begin(K_CRC_PIECES, 0); k_crc_pieces<<<gc, 256, 0, st>>>(d_x, (const u32 *)rec, sizeof(BlockRec) / 4, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
+    ctx->prof_begin(K_CRC_PIECES, (u64)*consumed); k_crc_pieces<<<gc, 256, 0, st>>>(d_x, (const u32 *)rec, sizeof(BlockRec) / 4, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp); LAUNCH_OK();
     ctx->prof_begin(K_CRC_FINAL, 0); k_crc_final<<<nb, 32, 0, st>>>((const u32 *)rec, sizeof(BlockRec) / 4, 0, 0, ctx->d_agg2.as<u32>(), parts_stride, xp256, ctx->d_crc.as<u32>()); LAUNCH_OK();
     B.T = ctx->d_T.as<u8>();
     B.len = ctx->d_len.as<u32>();
