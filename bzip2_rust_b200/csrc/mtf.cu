@@ -90,9 +90,13 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_summary(const u8 *Lall, cons
         u32 i = i0 + lane;
         bool in = i < e;
         bool nz = false, run_end = false;
+        const u32 chm = in ? (u32)L[i] : (0x100u | (u32)lane);
+        {   // last occurrence of every byte value: positions grow with the lane, so the highest lane of each value wins
+            const u32 peers = __match_any_sync(0xffffffffu, chm);
+            if (in && (peers >> lane) == 1u) slast[w][chm] = (int)i;
+        }
         if (in) {
-            u32 ch = L[i];
-            atomicMax(&slast[w][ch], (int)i);
+            u32 ch = chm;
             nz = is_nz(L, i, min_used);
             bool nz_next = (i + 1 >= n) ? true : (L[i + 1] != ch);
             run_end = !nz && nz_next;
