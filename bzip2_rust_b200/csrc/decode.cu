@@ -149,12 +149,11 @@ static int ibwt_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_keys, u8 *d
     u32 *P = ctx->d_SA.as<u32>();
     // P = rows sorted stably by their byte: one radix pass with digit = L[row]
     radix::RadixArgs a{};
-    a.T = B.T; a.len = B.len; a.cnt = B.len; a.sa_in = nullptr; a.sa_out = P;
-    a.thist = ctx->d_thist.as<u32>(); a.stride = B.stride; a.rtiles = rtiles; a.off = 0;
+    a.T = B.T; a.len = B.len; a.sa_out = P; a.thist = ctx->d_thist.as<u32>(); a.stride = B.stride; a.rtiles = rtiles;
     dim3 gr((B.max_n + radix::R_TILE - 1) / radix::R_TILE, B.nblk);
-    ctx->prof_begin(K_RADIX_HIST0, B.total_n * 5); radix::k_radix_hist<0><<<gr, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+    ctx->prof_begin(K_RADIX_HIST0, B.total_n * 5); radix::k_radix_hist<<<gr, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
     ctx->prof_begin(K_RADIX_SCAN, 0); radix::k_radix_scan<<<B.nblk, 256, 0, st>>>(a.thist, B.len, rtiles); LAUNCH_OK();
-    ctx->prof_begin(K_RADIX_SCATTER0, B.total_n * 9); radix::k_radix_scatter<0><<<gr, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
+    ctx->prof_begin(K_RADIX_SCATTER0, B.total_n * 9); radix::k_radix_scatter<<<gr, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
     dim3 gs((B.max_n / SPLIT + 2 + 255) / 256, B.nblk);
     ctx->prof_begin(K_IBWT_CHASE, B.total_n * 4); k_ibwt_chase<<<gs, 256, 0, st>>>(P, B.len, d_keys, B.stride, seglen, segnext, sstride); LAUNCH_OK();
     ctx->prof_begin(K_IBWT_RANK, 0); k_ibwt_rank<<<B.nblk, 32, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, vsplit, voff, vstride, nvisit); LAUNCH_OK();

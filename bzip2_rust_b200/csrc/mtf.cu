@@ -15,9 +15,9 @@
 //                 the MTF list at the chunk start is the byte values sorted by that, descending.
 //                 A short sequential pass turns the zero-run bookkeeping into per-chunk output
 //                 offsets and pending-zero counts.
-//   k_mtf_emit    one warp per chunk: sorts the 256 values into the start list, replays the chunk
-//                 with the list held as 8 bytes per lane, and writes final u16 symbols straight
-//                 at their output offsets.
+//   k_mtf_emit3   one warp per chunk: ranks the used values into the start list and replays the chunk
+//                 32 positions per step on the inverse list (mtf_emit3.cuh), writing final u16 symbols
+//                 straight at their output offsets.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(256) k_mtf_scan(const u32 *len, const u32 *use
     }
 }
 
-#include "mtf_emit.cuh"    // k_mtf_emit2: byte-serial replay (kept for A/B: BZ2B200_MTF_V2=1)
 #include "mtf_emit3.cuh"   // k_mtf_emit3: position-parallel replay, the version that is launched
 
 }  // namespace
@@ -214,10 +213,8 @@ int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, 
     if (!used_ready) { ctx->prof_begin(K_USED, ne_act); k_used<<<gfull, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, B.stride); LAUNCH_OK(); }
     ctx->prof_begin(K_MTF_SUMMARY, ne_act * 2); k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
     ctx->prof_begin(K_MTF_SCAN, ne_act * 2); k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
-    static const bool use_v2 = getenv("BZ2B200_MTF_V2") != nullptr;
     ctx->prof_begin(K_MTF_EMIT, ne_act * 3);
-    if (use_v2) k_mtf_emit2<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
-    else k_mtf_emit3<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
+    k_mtf_emit3<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
     LAUNCH_OK();
     return BZ2B200_OK;
 }

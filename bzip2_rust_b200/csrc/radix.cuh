@@ -1,17 +1,10 @@
 // radix.cuh -- three-kernel stable counting-sort pass (histogram -> scan -> scatter), one bzip2 block per blockIdx.y.
-// The inverse BWT (decode.cu) uses one MODE 0 pass; the forward BWT uses the one-kernel passes in sweep.cuh.
-//
-// MODE 0: initial sort of rotation indices; the digit of a pass is gathered from the block text
-//         (T[(sa+off) mod n]), so only the 4-byte index moves.
-// MODE 1: unresolved-list sort; element = (key64, val32), digit = 8 bits of the key.
-// A pass = k_radix_hist (per-tile digit counts) -> k_radix_scan (per block: counts -> scatter offsets)
-// -> k_radix_scatter (stable in-tile ranking with warp match, staged through shared memory so that
-// every digit run leaves the CTA as consecutive addresses).
-// Tile = 2048 elements (256 threads x 8): small enough for 4 CTAs per SM (the first version used 4096
-// elements and 150 registers, i.e. one CTA per SM; ncu showed 12% warp occupancy).
+// Used by the inverse BWT (decode.cu): P = rows sorted stably by their byte, i.e. one pass with digit = L[row].
+// (The forward BWT sorts with the one-kernel passes in sweep.cuh.)
+// Tile = 2048 elements (256 threads x 8): stable in-tile ranking with warp match, staged through shared memory so
+// that every digit run leaves the CTA as consecutive addresses.
 #pragma once
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace radix {
 
@@ -19,48 +12,26 @@ constexpr int R_IPT = 8;
 constexpr int R_TILE = BZ_THREADS * R_IPT;   // 2048
 
 struct RadixArgs {
-    const u8 *T; const u32 *len;   // text and block lengths
-    const u32 *cnt;                // element count per block (MODE 0: len, MODE 1: list count)
-    const u32 *sa_in; u32 *sa_out; // MODE 0 (sa_in == nullptr => identity)
-    const u64 *key_in; u64 *key_out; const u32 *val_in; u32 *val_out;   // MODE 1
+    const u8 *T; const u32 *len;   // digit source (one byte per row) and block lengths
+    u32 *sa_out;                   // [nblk][stride] sorted row indices
     u32 *thist;                    // [nblk][rtiles][256]
     u32 stride, rtiles;
-    int off;                       // MODE 0: byte offset of this digit within the rotation
-    int shift;                     // MODE 1: bit shift of this digit
 };
 
-template <int MODE>
-__device__ __forceinline__ int radix_digit(const RadixArgs &a, u32 b, u32 n, u32 idx, u32 &sa, u64 &key) {
-    if (MODE == 0) {
-        sa = a.sa_in ? a.sa_in[(size_t)b * a.stride + idx] : idx;
-        u32 p = sa + (u32)a.off;
-        if (p >= n) { p -= n; if (p >= n) p %= n; }    // off < 8: one subtraction except for blocks shorter than 8
-        return a.T[(size_t)b * a.stride + p];
-    } else {
-        key = a.key_in[(size_t)b * a.stride + idx];
-        return (int)((key >> a.shift) & 255);
-    }
-}
-
-template <int MODE>
 __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_hist(RadixArgs a) {
     u32 b = blockIdx.y, t = blockIdx.x;
-    u32 cnt = a.cnt[b];
-    u32 base = t * R_TILE;
-    if (base >= cnt) return;
     u32 n = a.len[b];
+    u32 base = t * R_TILE;
+    if (base >= n) return;
     __shared__ u32 h[8][256];
     for (int i = threadIdx.x; i < 8 * 256; i += BZ_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
+    const u8 *T = a.T + (size_t)b * a.stride;
     int w = threadIdx.x >> 5;
 #pragma unroll
     for (int r = 0; r < R_IPT; r++) {
         u32 idx = base + r * BZ_THREADS + threadIdx.x;
-        if (idx < cnt) {
-            u32 sa; u64 key;
-            int d = radix_digit<MODE>(a, b, n, idx, sa, key);
-            atomicAdd(&h[w][d], 1u);
-        }
+        if (idx < n) atomicAdd(&h[w][T[idx]], 1u);
     }
     __syncthreads();
     u32 s = 0;
@@ -89,14 +60,12 @@ static __global__ void __launch_bounds__(256) k_radix_scan(u32 *thist, const u32
     }
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_scatter(RadixArgs a) {
     u32 b = blockIdx.y, t = blockIdx.x;
-    u32 cnt = a.cnt[b];
-    u32 base = t * R_TILE;
-    if (base >= cnt) return;
     u32 n = a.len[b];
-    u32 tile_n = min((u32)R_TILE, cnt - base);
+    u32 base = t * R_TILE;
+    if (base >= n) return;
+    u32 tile_n = min((u32)R_TILE, n - base);
 
     __shared__ u32 wh[8 * 256];
     __shared__ u32 lbase[256];
@@ -104,25 +73,20 @@ __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_scatter(RadixArgs a) {
     __shared__ u32 ws[8];
     __shared__ u8 sdig[R_TILE];
     __shared__ u32 sval[R_TILE];
-    __shared__ u64 skey[MODE == 1 ? R_TILE : 1];
 
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 8 * 256; i += BZ_THREADS) wh[i] = 0;
     toff[threadIdx.x] = a.thist[((size_t)b * a.rtiles + t) * 256 + threadIdx.x];
     __syncthreads();
 
-    int dig[R_IPT]; u32 val[R_IPT]; u64 key[R_IPT]; u32 rnk[R_IPT];
+    const u8 *T = a.T + (size_t)b * a.stride;
+    int dig[R_IPT]; u32 val[R_IPT]; u32 rnk[R_IPT];
     // warp w owns elements [w*256, w*256+256) of the tile; round r covers 32 consecutive elements
 #pragma unroll
-    for (int r = 0; r < R_IPT; r++) {           // loads first: all independent
+    for (int r = 0; r < R_IPT; r++) {
         u32 e = w * (32 * R_IPT) + r * 32 + lane;
-        u32 idx = base + e;
-        dig[r] = 0x7fff; val[r] = 0; key[r] = 0;
-        if (e < tile_n) {
-            u32 sa = 0; u64 k = 0;
-            dig[r] = radix_digit<MODE>(a, b, n, idx, sa, k);
-            if (MODE == 0) val[r] = sa; else { key[r] = k; val[r] = a.val_in[(size_t)b * a.stride + idx]; }
-        }
+        dig[r] = 0x7fff; val[r] = base + e;
+        if (e < tile_n) dig[r] = T[base + e];
     }
 #pragma unroll
     for (int r = 0; r < R_IPT; r++) {           // stable ranking inside the warp's segment
@@ -153,7 +117,6 @@ __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_scatter(RadixArgs a) {
             u32 pos = lbase[d] + wh[w * 256 + d] + rnk[r];
             sdig[pos] = (u8)d;
             sval[pos] = val[r];
-            if (MODE == 1) skey[pos] = key[r];
         }
     }
     __syncthreads();
@@ -163,9 +126,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 4) k_radix_scatter(RadixArgs a) {
         u32 p = r * BZ_THREADS + threadIdx.x;
         if (p < tile_n) {
             int d = sdig[p];
-            u32 dst = toff[d] + (p - lbase[d]);
-            if (MODE == 0) a.sa_out[ob + dst] = sval[p];
-            else { a.key_out[ob + dst] = skey[p]; a.val_out[ob + dst] = sval[p]; }
+            a.sa_out[ob + toff[d] + (p - lbase[d])] = sval[p];
         }
     }
 }

@@ -9,8 +9,10 @@
  * Conventions
  *   - return 0 on success, negative BZ2B200_E_* otherwise; nothing ever unwinds or aborts
  *     across this boundary (the reference panics freely; a library must not).
- *   - functions WITHOUT the _dev suffix take HOST pointers; the library stages them
- *     through pinned memory and copies results back.  _dev functions take DEVICE
+ *   - functions WITHOUT the _dev suffix take HOST pointers and copy results back.
+ *     bz2b200_compress_stream uploads in chunks on its own stream while the first kernels
+ *     run and downloads finished output on another; pass page-locked buffers for full
+ *     overlap (pageable memory works, the copies then block).  _dev functions take DEVICE
  *     pointers on the context's GPU (used for HBM-resident measurement).
  *   - a context owns one GPU (streams, workspaces).  Calls on one context are serialised
  *     by an internal mutex; use one context per GPU for multi-GPU sharding.
