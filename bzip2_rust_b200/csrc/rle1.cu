@@ -128,7 +128,10 @@ struct ScanArgs {
 constexpr int SC_IPT = 16;
 constexpr int SC_TILE = BZ_THREADS * SC_IPT;
 
-__global__ void __launch_bounds__(BZ_THREADS) k_rle_scan(ScanArgs a) {
+#ifndef BZ_SCAN_MINB
+#define BZ_SCAN_MINB 5      /* 48 registers: five CTAs per SM hide the two look-back waits better than four (0.76 -> 0.67 ms) */
+#endif
+__global__ void __launch_bounds__(BZ_THREADS, BZ_SCAN_MINB) k_rle_scan(ScanArgs a) {
     __shared__ u32 s_tile;
     __shared__ int wsi[8];
     __shared__ u32 wsu[8];
