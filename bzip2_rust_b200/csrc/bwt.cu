@@ -126,7 +126,10 @@ __device__ __forceinline__ bool ticket_tile(const RefineArgs &a, u32 *s_ticket, 
 // --------------------------------------------------------------------------------------
 // step 2: groups of the 8-byte sort -> ranks and the first unresolved list
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BZ_THREADS) k_init_ranks(RefineArgs a) {
+#ifndef BZ_REFINE_MINB
+#define BZ_REFINE_MINB 5
+#endif
+__global__ void __launch_bounds__(BZ_THREADS, BZ_REFINE_MINB) k_init_ranks(RefineArgs a) {
     __shared__ u64 sk[RT + 2];          // sk[i] = key of row base - 1 + i
     __shared__ __align__(8) u8 fl[RT + 8];
     __shared__ u32 hd[RT_PAD];
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(BZ_THREADS) k_list_key(const u32 *cntp, const 
 }
 
 // Sorted list -> refined groups: SA rows and ranks rewritten, still-tied entries compacted into the next list.
-__global__ void __launch_bounds__(BZ_THREADS) k_list_refine(RefineArgs a) {
+__global__ void __launch_bounds__(BZ_THREADS, BZ_REFINE_MINB > 5 ? 5 : BZ_REFINE_MINB) k_list_refine(RefineArgs a) {
     __shared__ u64 sk[RT + 2];          // sk[i] = (head, key2) of list entry base - 1 + i
     __shared__ __align__(8) u8 fl[RT + 8];
     __shared__ u32 kgs[RT_PAD], kss[RT_PAD];

@@ -178,7 +178,15 @@ __device__ __forceinline__ void tile_body(const Args &a, u32 b, u32 t, u32 base,
 #undef SWEEP_DIGIT
 }
 
-constexpr int min_ctas(int MODE, int IPT) { return MODE == M_CARRY ? (IPT <= 8 ? 6 : 4) : (IPT <= 8 ? 4 : 3); }
+#ifndef BZ_SWEEP_MINB_G
+#define BZ_SWEEP_MINB_G 3
+#endif
+#ifndef BZ_SWEEP_MINB_L
+#define BZ_SWEEP_MINB_L 3
+#endif
+constexpr int min_ctas(int MODE, int IPT) {
+    return MODE == M_CARRY ? (IPT <= 8 ? 6 : 4) : (IPT <= 8 ? 4 : (MODE == M_GATHER ? BZ_SWEEP_MINB_G : BZ_SWEEP_MINB_L));
+}
 
 template <int MODE, int IPT>
 __global__ void __launch_bounds__(BZ_THREADS, min_ctas(MODE, IPT)) k_sweep(Args a) {
