@@ -246,7 +246,7 @@ int bz2b200_compress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int l
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     // knobs: windows per call (1 = upload everything, compress, download) and upload chunk size
     static const int n_windows = [] { const char *e = getenv("BZ2B200_E2E_WINDOWS"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
-    const size_t CHUNK = 8u << 20;
+    static const size_t CHUNK = [] { const char *e = getenv("BZ2B200_E2E_CHUNK_MB"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : v) << 20; }();
     size_t cap = bz2b200_compress_bound(n);
     BZ_CHECK(ctx->d_in.ensure(n + 64));
     BZ_CHECK(ctx->d_stream.ensure(cap + 64));
