@@ -1,0 +1,28 @@
+"""Property test of the CUDA path against the oracle: random and run-heavy inputs (run lengths around the RLE1
+thresholds 3/4/5 and 255/256, input ends in every phase of a run) must give the oracle's stream byte for byte."""
+import bz2
+
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+pytestmark = pytest.mark.gpu
+
+
+@st.composite
+def run_heavy(draw):
+    pieces = draw(st.lists(st.tuples(st.integers(0, 5), st.sampled_from([1, 2, 3, 4, 5, 6, 7, 50, 254, 255, 256, 259, 600])),
+                           min_size=1, max_size=40))
+    return b"".join(bytes([97 + v]) * n for v, n in pieces)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(data=st.one_of(st.binary(min_size=1, max_size=3000), run_heavy()), level=st.sampled_from([1, 9]))
+def test_engine_stream_equals_oracle_stream(engine, ref, data, level):
+    try:
+        want = ref.compress_stream(data, level, ref.SPEC_FAST)
+    except ref.RefPanic:
+        return
+    got = engine.compress(data, level)
+    assert got == want
+    assert bz2.decompress(got) == data
+    assert engine.decompress(got, max_out=len(data) + 1024) == data
