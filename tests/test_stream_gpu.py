@@ -138,3 +138,22 @@ def test_range_compress_and_merge_equals_single_stream(engine, ref):
             assert rc == 0, L.bz2b200_last_error(engine._h)
             parts.append((out[:(bits.value + 7) // 8].tobytes(), bits.value, list(crcs[:count])))
         assert bz.merge_streams(2, parts) == whole, split
+
+
+def test_windowed_host_path_gives_the_same_stream(engine):
+    """bz2b200_compress_stream split into several windows (BZ2B200_E2E_WINDOWS, read once per process): the chunked
+    upload, the scan that follows it and the partial downloads must not change a byte."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    data = corpus.text(40_000_000, 77)
+    want = hashlib.sha256(engine.compress(data, 9)).hexdigest()
+    code = ("import hashlib, sys; sys.path.insert(0, %r); import bzip2_rust_b200 as bz; from bzip2_rust_b200 import corpus; "
+            "print(hashlib.sha256(bz.Engine().compress(corpus.text(40_000_000, 77), 9)).hexdigest())"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for env in ({"BZ2B200_E2E_WINDOWS": "2"}, {"BZ2B200_E2E_WINDOWS": "3", "BZ2B200_E2E_CHUNK_MB": "3"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.stdout.strip().splitlines()[-1] == want, env
