@@ -15,9 +15,16 @@ def run_heavy(draw):
     return b"".join(bytes([97 + v]) * n for v, n in pieces)
 
 
-@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(data=st.one_of(st.binary(min_size=1, max_size=3000), run_heavy()), level=st.sampled_from([1, 9]))
 def test_engine_stream_equals_oracle_stream(engine, ref, data, level):
+    # an input that ends in four equal bytes makes the reference panic or emit an invalid stream (the
+    # restatement follows it there; the engine deliberately does not): only the round trip holds
+    if len(data) >= 4 and data[-4:] == data[-1:] * 4:
+        got = engine.compress(data, level)
+        assert bz2.decompress(got) == data
+        assert engine.decompress(got, max_out=len(data) + 1024) == data
+        return
     try:
         want = ref.compress_stream(data, level, ref.SPEC_FAST)
     except ref.RefPanic:
