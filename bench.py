@@ -522,6 +522,9 @@ def _main(args, real_stdout):
                      round((v[2] / 1e9) / (v[0] * 1e-3) / peak, 4) if v[0] > 0 else 0.0]
                     for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][0])],
         "verified_roundtrip_libbz2": verified,
+        # blocks (since the engine was created) that the reference's path selector (bwt_sort.rs:29) would have sent to its
+        # SA-IS fallback, counted on the device: 0 means the reference's output is well defined for the whole workload
+        "ref_path": {"blocks": int(eng.bwt_stats()["blocks_total"]), "sais": int(eng.bwt_stats()["ref_sais_blocks_total"])},
         "compressed_bytes": int(clen),
     }
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

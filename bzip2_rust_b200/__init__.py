@@ -163,7 +163,8 @@ class Engine:
     def bwt_stats(self):
         st = (C.c_uint64 * 8)()
         self._L.bz2b200_get_bwt_stats(self._h, C.byref(st))
-        return dict(blocks=st[0], rounds=st[2], list_sum=st[3])
+        return dict(blocks=st[0], rounds=st[2], list_sum=st[3], ref_sais_blocks=st[4], ref_sais_blocks_total=st[5],
+                    blocks_total=st[6])
 
     def rle2_mtf_encode(self, bwt):
         """rle2_mtf_encode (rle2_mtf.rs:23) -> (symbols u16[m] incl. EOB, freq u32[256], symbol map u16[<=17])."""

@@ -347,6 +347,28 @@ __global__ void __launch_bounds__(BZ_THREADS, BZ_REFINE_MINB > 5 ? 5 : BZ_REFINE
     }
 }
 
+// Path selector of the reference (bwt_sort.rs:29, lms_complexity sais_fallback.rs:821-829, LMS typing :59-131): a block
+// longer than 5000 bytes goes to the SA-IS fallback when its first 5000 bytes hold at most 1499 LMS positions (the
+// sentinel counts as one).  The engine always computes the true rotation BWT; this only COUNTS the
+// blocks the reference would have routed to its fallback, so that a run can report them.  One thread per block.
+__global__ void __launch_bounds__(128) k_ref_path(const u8 *T, const u32 *len, u32 stride, u32 nblk, u32 *sais_blocks) {
+    u32 b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= nblk) return;
+    u32 n = len[b];
+    if (n <= 5000) return;
+    const u8 *x = T + (size_t)b * stride;
+    u32 lms = 1;                                                // the sentinel
+    bool cur_s = false;                                         // the last byte is L: the sentinel is smaller
+    u32 prev = x[4999];
+    for (int k = 4998; k >= 0; k--) {
+        u32 el = x[k];
+        if (el < prev) cur_s = true;
+        else if (el > prev) { if (cur_s) { lms++; cur_s = false; } }
+        prev = el;
+    }
+    if (lms <= 1499) atomicAdd(sais_blocks, 1u);
+}
+
 // used-byte bitmap of every block from its byte histogram (rle2_mtf.rs:26-39 builds the same set by scanning)
 __global__ void __launch_bounds__(256) k_used_from_hist(const u32 *counts, u32 cstride, u32 *usedbits) {
     u32 b = blockIdx.x;
@@ -400,9 +422,11 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key, u32 *d
     BZ_CHECK(ctx->d_KEYB.ensure(ne * 8));
     BZ_CHECK(ctx->d_thist.ensure((size_t)B.nblk * tiles_min * 256 * 4));
     BZ_CHECK(ctx->d_tagg.ensure((size_t)B.nblk * tiles_min * 8));
-    BZ_CHECK(ctx->d_cnt.ensure((size_t)B.nblk * 2 * 4));
+    BZ_CHECK(ctx->d_cnt.ensure((size_t)B.nblk * 2 * 4 + 16));
     BZ_CHECK(ctx->d_R.ensure(((size_t)B.nblk * DSTRIDE + NTICKET) * 4));
     BZ_CHECK(ctx->h_small.ensure((size_t)B.nblk * 4 + 64));
+    u32 *d_sais = ctx->d_cnt.as<u32>() + (size_t)B.nblk * 2;
+    BZ_CHECK(cudaMemsetAsync(d_sais, 0, 4, ctx->stream));
     u32 *SAa = ctx->d_SA.as<u32>(), *SAb = ctx->d_SA2.as<u32>(), *RANK = ctx->d_RANK.as<u32>();
     u64 *L0 = ctx->d_KEYA.as<u64>(), *L1 = ctx->d_KEYB.as<u64>();
     u32 *tstate = ctx->d_thist.as<u32>();
@@ -422,6 +446,7 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key, u32 *d
     // ---- 1. initial 8-byte LSD sort (implicit keys) ----
     // every pass has the same digit totals: the block's byte histogram (each byte is digit p of exactly one rotation)
     ctx->prof_begin(K_BYTE_HIST, ne_act); sweep::k_byte_hist<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, dcounts, B.stride, DSTRIDE); LAUNCH_OK();
+    ctx->prof_begin(K_REF_PATH, (u64)B.nblk * 5000); k_ref_path<<<(B.nblk + 127) / 128, 128, 0, st>>>(B.T, B.len, B.stride, (u32)B.nblk, d_sais); LAUNCH_OK();
     if (d_usedbits) { ctx->prof_begin(K_USED, (u64)B.nblk * 1024); k_used_from_hist<<<B.nblk, 256, 0, st>>>(dcounts, DSTRIDE, d_usedbits); LAUNCH_OK(); }
     ctx->prof_begin(K_DIGIT_SCAN, (u64)B.nblk * DSTRIDE * 4); sweep::k_digit_scan<<<B.nblk * 8, 256, 0, st>>>(dcounts); LAUNCH_OK();
     u32 *bufs[2] = {SAa, SAb};
@@ -456,6 +481,7 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key, u32 *d
     u32 *h_cnt = ctx->h_small.as<u32>();
     const int passes = 5;                      // bits [20, 60) of the packed element
     u64 rounds = 0, listsum = 0;
+    BZ_CHECK(cudaMemcpyAsync(h_cnt + B.nblk, d_sais, 4, cudaMemcpyDeviceToHost, st));     // arrives with the first round's counts
     for (u32 h = 8;; h *= 2) {
         BZ_CHECK(cudaMemcpyAsync(h_cnt, cnt_cur, (size_t)B.nblk * 4, cudaMemcpyDeviceToHost, st));
         BZ_CHECK(cudaStreamSynchronize(st));
@@ -496,5 +522,8 @@ int bz_bwt_batch(bz2b200_ctx *ctx, const Batch &B, u8 *d_bwt, u32 *d_key, u32 *d
     // ---- 4. output ----
     ctx->prof_begin(K_BWT_OUT, ne_act * 6); k_bwt_out<<<gfull, BZ_THREADS, 0, st>>>(B.T, B.len, SA, RANK, d_bwt, d_key, B.stride); LAUNCH_OK();
     ctx->bwt_stats[0] = (u64)B.nblk; ctx->bwt_stats[1] = ne_act; ctx->bwt_stats[2] = rounds; ctx->bwt_stats[3] = listsum;
+    ctx->bwt_stats[4] = h_cnt[B.nblk];                           // blocks of this batch the reference would send to SA-IS
+    ctx->bwt_stats[5] += h_cnt[B.nblk];                          // ... and since the context was created
+    ctx->bwt_stats[6] += (u64)B.nblk;
     return BZ2B200_OK;
 }

@@ -152,7 +152,8 @@ int  bz2b200_kernel_stats(bz2b200_ctx *ctx, int idx, char name[64], double *ms, 
                           uint64_t *bytes);
 void bz2b200_reset_kernel_stats(bz2b200_ctx *ctx);
 /* statistics of the last BWT batch: [0]=blocks [1]=sum n [2]=max doubling rounds
- * [3]=sum over rounds of unresolved list lengths */
+ * [3]=sum over rounds of unresolved list lengths [4]=blocks the reference's path selector (bwt_sort.rs:29) would have
+ * sent to its SA-IS fallback; since the context was created: [5]=such blocks [6]=all blocks */
 int  bz2b200_get_bwt_stats(const bz2b200_ctx *ctx, uint64_t st[8]);
 
 #ifdef __cplusplus

@@ -61,3 +61,15 @@ def test_inverse_property_at_full_size(engine, ref):
     blk = corpus.mix1m(1)[:899_986].tobytes()
     key, bwt = engine.bwt_encode(blk)
     assert ref.bwt_decode(key, bwt) == blk
+
+
+def test_reference_path_selector_count(engine, ref):
+    """k_ref_path counts the blocks the reference would route to its SA-IS fallback (bwt_sort.rs:29): longer than 5000
+    bytes and at most 1499 LMS positions (sentinel included) in the first 5000."""
+    blocks = [corpus.text(300_000, 5).tobytes(), corpus.random_walk(300_000, 6).tobytes(),
+              corpus.random_bytes(200_000, 7).tobytes(), bytes(range(256)) * 40, b"ab" * 4000,
+              corpus.text(4000, 8).tobytes(), corpus.repetitive(100_000, 9).tobytes()]
+    want = sum(1 for b in blocks if len(b) > 5000 and ref.lms_count(b) <= 1499)
+    assert 0 < want < len(blocks)
+    engine.bwt_encode_batch(blocks)
+    assert engine.bwt_stats()["ref_sais_blocks"] == want
