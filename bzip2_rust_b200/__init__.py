@@ -164,7 +164,7 @@ class Engine:
         st = (C.c_uint64 * 8)()
         self._L.bz2b200_get_bwt_stats(self._h, C.byref(st))
         return dict(blocks=st[0], rounds=st[2], list_sum=st[3], ref_sais_blocks=st[4], ref_sais_blocks_total=st[5],
-                    blocks_total=st[6])
+                    blocks_total=st[6], big_sum=st[7])
 
     def rle2_mtf_encode(self, bwt):
         """rle2_mtf_encode (rle2_mtf.rs:23) -> (symbols u16[m] incl. EOB, freq u32[256], symbol map u16[<=17])."""
@@ -229,7 +229,7 @@ class Engine:
     def rle1_split(self, data, level=9):
         """RLE1Block iterator (rle1.rs:245-264) for the whole input -> list of (crc, block bytes, in_start, in_end)."""
         a = _np_u8(data)
-        cap_blocks = a.size // (level * 100000 - 19 - 8) + 4
+        cap_blocks = (a.size * 5 // 4) // (level * 100000 - 19 - 8) + 4      # RLE1 can turn 4 input bytes into 5
         cap = a.size + a.size // 4 + 1024
         out = np.zeros(cap, dtype=np.uint8)
         roff = np.zeros(cap_blocks + 1, dtype=np.uint64)
@@ -265,7 +265,7 @@ class Engine:
         """Block start offsets of the whole stream (n+1 entries, last = len).  `dev_ptr` = the data already on
         this GPU (raw device pointer), otherwise `data` is uploaded window by window."""
         n = data if dev_ptr is not None else _np_u8(data).size
-        cap = n // (level * 100000 - 19 - 8) + 8
+        cap = (n * 5 // 4) // (level * 100000 - 19 - 8) + 8
         starts = np.zeros(cap + 1, dtype=np.uint64)
         nb = C.c_uint32()
         if dev_ptr is not None:

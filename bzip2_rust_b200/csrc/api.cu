@@ -24,6 +24,7 @@ extern "C" {
 const char *bz2b200_version(void) { return "bz2b200 0.1 (sm_100a)"; }
 
 int bz2b200_create(int device, bz2b200_ctx **out) {
+    BZ_API_TRY
     if (!out) return BZ2B200_E_ARG;
     *out = nullptr;
     int ndev = 0;
@@ -43,12 +44,14 @@ int bz2b200_create(int device, bz2b200_ctx **out) {
     cudaEventCreate(&ctx->ev_total[1]);
     *out = ctx;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 void bz2b200_destroy(bz2b200_ctx *ctx) { delete ctx; }
 const char *bz2b200_last_error(const bz2b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t bz2b200_launch_count(const bz2b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void bz2b200_set_timing(bz2b200_ctx *ctx, int on) { if (ctx) { ctx->timing = on != 0; ctx->prof_level = on; } }
 int bz2b200_kernel_stats(bz2b200_ctx *ctx, int idx, char name[64], double *ms, uint64_t *launches, uint64_t *bytes) {
+    BZ_API_TRY
     if (!ctx || idx < 0 || idx >= K_COUNT || !name || !ms || !launches || !bytes) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaSetDevice(ctx->device);
@@ -57,6 +60,7 @@ int bz2b200_kernel_stats(bz2b200_ctx *ctx, int idx, char name[64], double *ms, u
     strncpy(name, kKernelNames[idx], 63); name[63] = 0;
     *ms = ctx->kstat[idx].ms; *launches = ctx->kstat[idx].launches; *bytes = ctx->kstat[idx].bytes;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 void bz2b200_reset_kernel_stats(bz2b200_ctx *ctx) {
     if (!ctx) return;
@@ -67,14 +71,18 @@ void bz2b200_reset_kernel_stats(bz2b200_ctx *ctx) {
     for (int i = 0; i < K_COUNT; i++) ctx->kstat[i] = KStat();
 }
 int bz2b200_get_timing(const bz2b200_ctx *ctx, float ms[8]) {
+    BZ_API_TRY
     if (!ctx || !ms) return BZ2B200_E_ARG;
     memcpy(ms, ctx->stage_ms, sizeof(float) * 8);
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 int bz2b200_get_bwt_stats(const bz2b200_ctx *ctx, uint64_t st[8]) {
+    BZ_API_TRY
     if (!ctx || !st) return BZ2B200_E_ARG;
     memcpy(st, ctx->bwt_stats, sizeof(u64) * 8);
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 }  // extern "C"
@@ -160,6 +168,7 @@ extern "C" {
 
 int bz2b200_bwt_encode_batch(bz2b200_ctx *ctx, int nblk, const uint8_t *const *in, const uint32_t *n,
                              uint8_t *const *bwt, uint32_t *key) {
+    BZ_API_TRY
     if (!ctx || nblk < 0 || (nblk && (!in || !n || !bwt || !key))) return BZ2B200_E_ARG;
     if (nblk == 0) return BZ2B200_OK;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -173,12 +182,15 @@ int bz2b200_bwt_encode_batch(bz2b200_ctx *ctx, int nblk, const uint8_t *const *i
     if (rc) return rc;
     BZ_CHECK(cudaMemcpyAsync(key, ctx->d_key.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
     return fetch_blocks<u8>(ctx, nblk, ctx->d_bwt.as<u8>(), B.stride, n, bwt);
+    BZ_API_CATCH
 }
 
 int bz2b200_bwt_encode(bz2b200_ctx *ctx, const uint8_t *in, uint32_t n, uint8_t *bwt, uint32_t *key) {
+    BZ_API_TRY
     const uint8_t *ins[1] = {in};
     uint8_t *outs[1] = {bwt};
     return bz2b200_bwt_encode_batch(ctx, 1, ins, &n, outs, key);
+    BZ_API_CATCH
 }
 
 }  // extern "C"
@@ -203,6 +215,7 @@ static void symmap_from_used(const u32 ub[8], uint16_t symmap[17], int *nmap) {
 
 extern "C" int bz2b200_mtf_rle2(bz2b200_ctx *ctx, const uint8_t *bwt, uint32_t n, uint16_t *sym, uint32_t *m,
                                 uint32_t freq[256], uint16_t symmap[17], int *nmap) {
+    BZ_API_TRY
     if (!ctx || !bwt || !sym || !m || !freq || !symmap || !nmap || n == 0) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -225,6 +238,7 @@ extern "C" int bz2b200_mtf_rle2(bz2b200_ctx *ctx, const uint8_t *bwt, uint32_t n
     BZ_CHECK(cudaStreamSynchronize(ctx->stream));
     symmap_from_used(ub, symmap, nmap);
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 // ------------------------------------------------------------------------------------------
@@ -263,6 +277,7 @@ int bz_compress_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_crc, HufOut
 extern "C" int bz2b200_compress_blocks(bz2b200_ctx *ctx, int nblk, const uint8_t *const *blk, const uint32_t *len,
                                        const uint32_t *crc, uint8_t *const *out, const size_t *out_cap,
                                        uint64_t *out_bits) {
+    BZ_API_TRY
     if (!ctx || nblk < 0 || (nblk && (!blk || !len || !crc || !out || !out_cap || !out_bits))) return BZ2B200_E_ARG;
     if (nblk == 0) return BZ2B200_OK;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -278,17 +293,20 @@ extern "C" int bz2b200_compress_blocks(bz2b200_ctx *ctx, int nblk, const uint8_t
     BZ_CHECK(cudaMemcpyAsync(out_bits, H.d_bits, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
     BZ_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < nblk; i++) {
+        if (out_bits[i] == ~0ull) { ctx->err = "huffman: packed block exceeds its slot"; return BZ2B200_E_CAP; }
         size_t nb = (size_t)((out_bits[i] + 7) / 8);
         if (nb > out_cap[i]) return BZ2B200_E_CAP;
         BZ_CHECK(cudaMemcpyAsync(out[i], H.d_out + (size_t)i * H.out_stride, nb, cudaMemcpyDeviceToHost, ctx->stream));
     }
     BZ_CHECK(cudaStreamSynchronize(ctx->stream));
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 extern "C" int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m, const uint32_t freq[256],
                                const uint16_t *symmap, int nmap, uint8_t *out, size_t out_cap, uint64_t *out_bits,
                                uint8_t *lengths, uint8_t *selectors, int *table_count) {
+    BZ_API_TRY
     if (!ctx || !sym || !freq || !symmap || !out || !out_bits || m < 2 || m > BZ2B200_MAX_BLOCK + 1 || nmap < 2 || nmap > 17)
         return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -324,6 +342,7 @@ extern "C" int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m
     BZ_CHECK(cudaMemcpyAsync(out_bits, H.d_bits, 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaMemcpyAsync(misc, H.d_ntab, 32, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
+    if (*out_bits == ~0ull) { ctx->err = "huffman: packed block exceeds its slot"; return BZ2B200_E_CAP; }
     size_t nb = (size_t)((*out_bits + 7) / 8);
     if (nb > out_cap) return BZ2B200_E_CAP;
     BZ_CHECK(cudaMemcpyAsync(out, H.d_out, nb, cudaMemcpyDeviceToHost, st));
@@ -332,4 +351,5 @@ extern "C" int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m
     BZ_CHECK(cudaStreamSynchronize(st));
     if (table_count) *table_count = (int)misc[0];
     return BZ2B200_OK;
+    BZ_API_CATCH
 }

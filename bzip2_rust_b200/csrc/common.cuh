@@ -6,6 +6,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <new>
 #include "../../include/bz2b200.h"
 
 typedef uint8_t u8;
@@ -21,6 +22,10 @@ typedef uint64_t u64;
             return BZ2B200_E_CUDA;                                                         \
         }                                                                                  \
     } while (0)
+
+// No exception may cross the C ABI (include/bz2b200.h): std::vector / std::string growth inside the entry points can throw.
+#define BZ_API_TRY try {
+#define BZ_API_CATCH } catch (const std::bad_alloc &) { return BZ2B200_E_NOMEM; } catch (...) { return BZ2B200_E_CUDA; }
 
 // Grow-only device / pinned buffers.
 struct DevBuf {
@@ -73,8 +78,8 @@ struct Batch {
     u64 total_n;       // sum of block lengths (host copy, for profiling byte counts)
 };
 
-enum KernelId { K_RADIX_HIST0, K_RADIX_SCAN, K_RADIX_SCATTER0, K_REF_PATH, K_BYTE_HIST, K_DIGIT_SCAN, K_SWEEP_GATHER, K_SWEEP_CARRY, K_SWEEP_LIST, K_INIT_RANKS, K_LIST_KEY, K_LIST_REFINE, K_BWT_OUT, K_USED, K_MTF_SUMMARY, K_MTF_SCAN, K_MTF_EMIT, K_HUF_INIT, K_HUF_SELECT, K_HUF_LENGTHS, K_HUF_GBITS, K_HUF_LAYOUT, K_HUF_EMIT, K_RLE_SCAN, K_RLE_CHAIN, K_RLE_EMIT, K_CRC_PIECES, K_CRC_FINAL, K_CONCAT, K_FOOTER, K_DEC_MISC, K_DEC_MAGIC, K_DEC_HEADER, K_DEC_BOUNDS, K_DEC_SYMS, K_DEC_CHUNKS, K_DEC_CHUNK_SCAN, K_IBWT_CHASE, K_IBWT_RANK, K_IBWT_WRITE, K_DEC_RLE1_COUNT, K_DEC_RLE1_WRITE, K_COUNT };
-static const char *const kKernelNames[] = { "k_radix_hist0", "k_radix_scan", "k_radix_scatter0", "k_ref_path", "k_byte_hist", "k_digit_scan", "k_sweep_gather", "k_sweep_carry", "k_sweep_list", "k_init_ranks", "k_list_key", "k_list_refine", "k_bwt_out", "k_used", "k_mtf_summary", "k_mtf_scan", "k_mtf_emit", "k_huf_init", "k_huf_select", "k_huf_lengths", "k_huf_gbits", "k_huf_layout", "k_huf_emit", "k_rle_scan", "k_rle_chain", "k_rle_emit", "k_crc_pieces", "k_crc_final", "k_concat", "k_footer", "k_dec_misc", "k_dec_find_magic", "k_dec_header", "k_dec_bounds", "k_dec_syms", "k_dec_chunks", "k_dec_chunk_scan", "k_ibwt_chase", "k_ibwt_rank", "k_ibwt_write", "k_dec_rle1_count", "k_dec_rle1_write" };
+enum KernelId { K_RADIX_HIST0, K_RADIX_SCAN, K_RADIX_SCATTER0, K_REF_PATH, K_BYTE_HIST, K_DIGIT_SCAN, K_SWEEP_GATHER, K_SWEEP_CARRY, K_SWEEP_LIST, K_INIT_RANKS, K_LIST_KEY, K_LIST_REFINE, K_REFINE_LOCAL, K_BWT_OUT, K_USED, K_MTF_SUMMARY, K_MTF_SCAN, K_MTF_EMIT, K_HUF_INIT, K_HUF_SELECT, K_HUF_LENGTHS, K_HUF_GBITS, K_HUF_LAYOUT, K_HUF_EMIT, K_RLE_SCAN, K_RLE_CHAIN, K_RLE_EMIT, K_CRC_PIECES, K_CRC_FINAL, K_CONCAT, K_FOOTER, K_DEC_MISC, K_DEC_MAGIC, K_DEC_HEADER, K_DEC_BOUNDS, K_DEC_SYMS, K_DEC_CHUNKS, K_DEC_CHUNK_SCAN, K_IBWT_CHASE, K_IBWT_RANK, K_IBWT_WRITE, K_DEC_RLE1_COUNT, K_DEC_RLE1_WRITE, K_COUNT };
+static const char *const kKernelNames[] = { "k_radix_hist0", "k_radix_scan", "k_radix_scatter0", "k_ref_path", "k_byte_hist", "k_digit_scan", "k_sweep_gather", "k_sweep_carry", "k_sweep_list", "k_init_ranks", "k_list_key", "k_list_refine", "k_refine_local", "k_bwt_out", "k_used", "k_mtf_summary", "k_mtf_scan", "k_mtf_emit", "k_huf_init", "k_huf_select", "k_huf_lengths", "k_huf_gbits", "k_huf_layout", "k_huf_emit", "k_rle_scan", "k_rle_chain", "k_rle_emit", "k_crc_pieces", "k_crc_final", "k_concat", "k_footer", "k_dec_misc", "k_dec_find_magic", "k_dec_header", "k_dec_bounds", "k_dec_syms", "k_dec_chunks", "k_dec_chunk_scan", "k_ibwt_chase", "k_ibwt_rank", "k_ibwt_write", "k_dec_rle1_count", "k_dec_rle1_write" };
 
 struct KStat { double ms = 0; u64 launches = 0; u64 bytes = 0; };
 struct PendingEv { int id; u64 bytes; cudaEvent_t a, b; };
@@ -88,8 +93,17 @@ struct Arrival {
     size_t waited;       // events the compute stream already waits for
 };
 
+// Pending state of the three-phase sharding entry points (shard.cu): scan -> plan -> compress on one window.
+struct ShardPlan {
+    bool scanned = false;
+    const u8 *d_win = nullptr; size_t win_lo = 0, win_len = 0, n_total = 0; int level = 0;
+    bool planned = false;
+    bool eof = false; u32 off_from = 0, stop_rel = 0, s0 = 0, nb = 0;
+};
+
 struct bz2b200_ctx {
     int device = 0;
+    ShardPlan shard;                 // guarded by `mu` like everything else in the context
     cudaStream_t stream = nullptr;
     cudaStream_t s_up = nullptr, s_down = nullptr;      // host-buffer pipelining (stream.cu)
     std::vector<cudaEvent_t> up_ev;
@@ -99,6 +113,7 @@ struct bz2b200_ctx {
     u64 launches = 0;
     bool timing = false;
     bool dec_attr_done = false;      // k_dec_bounds opted in to > 48 KB of dynamic shared memory on this device
+    bool loc_attr_done = false;      // k_refine_local likewise
     float stage_ms[8] = {0};
     u64 bwt_stats[8] = {0};
     cudaEvent_t ev[8] = {nullptr};
@@ -203,6 +218,35 @@ __device__ __forceinline__ int block_excl_max(int v, int *ws, int &total) {
     int prev = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) prev = -1;
     return max(wbase, prev);
+}
+// Exclusive running min FROM THE RIGHT over the threads of a CTA: min of v over all higher threads
+// (identity = 0x7fffffff). `ws` = 8+ ints of scratch. All threads call.
+__device__ __forceinline__ int block_excl_min_rev(int v, int *ws, int &total) {
+    const int INF = 0x7fffffff;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_down_sync(0xffffffffu, inc, o);
+        if (lane + o < 32) inc = min(inc, t);
+    }
+    __syncthreads();
+    if (lane == 0) ws[w] = inc;
+    __syncthreads();
+    int wv = (lane < (int)(blockDim.x >> 5)) ? ws[lane] : INF;
+    int winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_down_sync(0xffffffffu, winc, o);
+        if (lane + o < 32) winc = min(winc, t);
+    }
+    int wnext = __shfl_down_sync(0xffffffffu, winc, 1);
+    if (lane == 31) wnext = INF;
+    int wbase = __shfl_sync(0xffffffffu, wnext, w);
+    total = __shfl_sync(0xffffffffu, winc, 0);
+    int nxt = __shfl_down_sync(0xffffffffu, inc, 1);
+    if (lane == 31) nxt = INF;
+    return min(wbase, nxt);
 }
 #endif
 

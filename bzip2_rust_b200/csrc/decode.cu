@@ -163,6 +163,7 @@ static int ibwt_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_keys, u8 *d
 }
 
 extern "C" int bz2b200_bwt_decode(bz2b200_ctx *ctx, uint32_t key, const uint8_t *bwt, uint32_t n, uint8_t *out) {
+    BZ_API_TRY
     if (!ctx || !bwt || !out || n == 0 || key >= n) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -178,10 +179,12 @@ extern "C" int bz2b200_bwt_decode(bz2b200_ctx *ctx, uint32_t key, const uint8_t 
     BZ_CHECK(cudaMemcpyAsync(out, ctx->d_bwt.p, n, cudaMemcpyDeviceToHost, ctx->stream));
     BZ_CHECK(cudaStreamSynchronize(ctx->stream));
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
                                          size_t *out_len) {
+    BZ_API_TRY
     if (!ctx || !in || !out_len || (!out && out_cap) || n < 14) return BZ2B200_E_ARG;
     if (in[0] != 'B' || in[1] != 'Z' || in[2] != 'h' || in[3] < '1' || in[3] > '9') return BZ2B200_E_FORMAT;   // decompress.rs:46-62
     int level = in[3] - '0';
@@ -315,4 +318,5 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     for (u32 k = 0; k < nb; k++)
         if (crcs[k] != db[k].crc) { ctx->err = "decode: CRC mismatch in block " + std::to_string(k); return BZ2B200_E_CRC; }   // enforced, unlike decompress.rs:379-386
     return BZ2B200_OK;
+    BZ_API_CATCH
 }

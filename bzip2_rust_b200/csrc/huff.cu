@@ -375,14 +375,18 @@ __global__ void __launch_bounds__(256) k_huf_layout(HufWs W, const u32 *usedbits
     }
     if (threadIdx.x == 0) {
         mi[3] = sel_start; mi[4] = data_start; mi[5] = sel_total;
-        bits_out[b] = (u64)data_start + carry;
+        u64 total_bits = (u64)data_start + carry;
+        // codes can be 17 bits long: a block that does not fit its slot is reported, never written past it
+        // (~0 = "does not fit"; the host turns it into BZ2B200_E_CAP, k_huf_emit skips the block)
+        bits_out[b] = (total_bits + 7) / 8 + 16 > (u64)out_stride ? ~0ull : total_bits;
     }
 }
 
 // ---- k_huf_emit: thread per group -------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_huf_emit(const u16 *sym, const u32 *m_in, HufWs W, u32 stride, u8 *outb,
-                                                  size_t out_stride) {
+                                                  size_t out_stride, const u64 *bits_out) {
     u32 b = blockIdx.y;
+    if (bits_out[b] == ~0ull) return;                           // k_huf_layout: the block does not fit its slot
     u32 m = m_in[b];
     u32 g0 = blockIdx.x * 256;
     u32 G = (m + BZ_GROUP - 1) / BZ_GROUP;
@@ -482,7 +486,7 @@ int bz_huf_batch(bz2b200_ctx *ctx, const Batch &B, const u16 *d_sym, const u32 *
     ctx->prof_begin(K_HUF_LAYOUT, (u64)B.nblk * 4096); k_huf_layout<<<B.nblk, 256, 0, st>>>(W, usedbits, emit_header, d_crc, d_key, ctx->d_out.as<u8>(), out_stride,
                                          ctx->d_outbits.as<u64>());
     LAUNCH_OK();
-    ctx->prof_begin(K_HUF_EMIT, ne_act * 3); k_huf_emit<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride, ctx->d_out.as<u8>(), out_stride); LAUNCH_OK();
+    ctx->prof_begin(K_HUF_EMIT, ne_act * 3); k_huf_emit<<<gg, 256, 0, st>>>(d_sym, d_m, W, B.stride, ctx->d_out.as<u8>(), out_stride, ctx->d_outbits.as<u64>()); LAUNCH_OK();
     out.d_out = ctx->d_out.as<u8>();
     out.d_bits = ctx->d_outbits.as<u64>();
     out.out_stride = out_stride;

@@ -21,22 +21,6 @@ int bz_concat_blocks(bz2b200_ctx *ctx, const HufOut &H, u32 nb, const u64 *hoff,
 int bz_shift_bits(bz2b200_ctx *ctx, const u8 *d_src, u64 nbits, int phase, u8 *d_dst);
 
 namespace {
-struct ShardPlan {
-    // scan state
-    bool scanned = false;
-    const u8 *d_win = nullptr; size_t win_lo = 0, win_len = 0, n_total = 0; int level = 0;
-    // chain state
-    bool planned = false;
-    bool eof = false; u32 off_from = 0, stop_rel = 0, s0 = 0, nb = 0;
-};
-std::mutex g_mu;
-std::vector<std::pair<bz2b200_ctx *, ShardPlan>> g_plans;      // one pending plan per context
-ShardPlan &plan_of(bz2b200_ctx *ctx) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    for (auto &p : g_plans) if (p.first == ctx) return p.second;
-    g_plans.emplace_back(ctx, ShardPlan());
-    return g_plans.back().second;
-}
 constexpr u32 MAX_SHARD_BLOCKS = 4096;
 
 int do_scan(bz2b200_ctx *ctx, ShardPlan &P, const u8 *d_win, size_t win_lo, size_t win_len, size_t n_total, int level) {
@@ -56,11 +40,13 @@ extern "C" {
 // Phase 1 (needs no hand-off): scans d_win[0 .. win_len) = bytes [win_lo, win_lo + win_len) of the stream.
 int bz2b200_shard_scan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
                            int level) {
+    BZ_API_TRY
     if (!ctx || !d_win || level < 1 || level > 9 || win_lo + win_len > n_total || win_len > 0xFFFFFF00ull || win_len == 0)
         return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
-    return do_scan(ctx, plan_of(ctx), d_win, win_lo, win_len, n_total, level);
+    return do_scan(ctx, ctx->shard, d_win, win_lo, win_len, n_total, level);
+    BZ_API_CATCH
 }
 
 // Phase 2: chains every block whose first byte lies in [start, stop_at) (absolute offsets; `start` must be a true
@@ -68,12 +54,13 @@ int bz2b200_shard_scan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo
 // just scanned.  BZ2B200_E_CAP: the window ends before the last such block does (lengthen it and call again).
 int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo, size_t win_len, size_t n_total,
                            int level, size_t start, size_t stop_at, size_t *next_start, uint32_t *nblocks) {
+    BZ_API_TRY
     if (!ctx || !d_win || !next_start || !nblocks || level < 1 || level > 9 || win_lo + win_len > n_total ||
         win_len > 0xFFFFFF00ull)
         return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
-    ShardPlan &P = plan_of(ctx);
+    ShardPlan &P = ctx->shard;
     P.planned = false;
     *nblocks = 0;
     // the previous rank's last block may already cover this whole shard: nothing to do, pass the chain on
@@ -100,16 +87,18 @@ int bz2b200_shard_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_win, size_t win_lo
     *nblocks = nb;
     P.planned = true; P.eof = eof; P.off_from = off_from; P.stop_rel = stop_rel; P.s0 = s0; P.nb = nb;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 // Phase 3: compresses the blocks of the preceding bz2b200_shard_plan_dev call (same context, window still
 // resident).  d_out receives one bit string (no stream header/footer); block_crcs[nblocks].
 int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
                                uint32_t *block_crcs) {
-    if (!ctx || !d_out || !out_bits) return BZ2B200_E_ARG;
+    BZ_API_TRY
+    if (!ctx || !d_out || !out_bits || ((uintptr_t)d_out & 3u)) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
-    ShardPlan &P = plan_of(ctx);
+    ShardPlan &P = ctx->shard;
     if (!P.planned) { ctx->err = "shard_compress: no pending plan"; return BZ2B200_E_ARG; }
     P.planned = false;
     *out_bits = 0;
@@ -148,6 +137,7 @@ int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap,
         hoff.resize(cnt);
         u64 maxbits = 0;
         for (u32 k = 0; k < cnt; k++) {
+            if (hbits[k] == ~0ull) { ctx->err = "huffman: packed block exceeds its slot"; return BZ2B200_E_CAP; }
             hoff[k] = bitpos; bitpos += hbits[k]; maxbits = std::max(maxbits, hbits[k]);
             block_crcs[first + k] = hcrc[k];
         }
@@ -162,15 +152,18 @@ int bz2b200_shard_compress_dev(bz2b200_ctx *ctx, uint8_t *d_out, size_t out_cap,
     }
     *out_bits = bitpos;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 // d_dst = d_src shifted right by `phase` bits (0..7): byte k of d_dst then lines up with byte (offset/8 + k)
 // of the final stream when phase = offset % 8.  d_dst needs (nbits + phase + 7)/8 + 8 bytes.
 int bz2b200_shift_bits_dev(bz2b200_ctx *ctx, const uint8_t *d_src, uint64_t nbits, int phase, uint8_t *d_dst) {
-    if (!ctx || !d_src || !d_dst || phase < 0 || phase > 7) return BZ2B200_E_ARG;
+    BZ_API_TRY
+    if (!ctx || !d_src || !d_dst || phase < 0 || phase > 7 || (((uintptr_t)d_src | (uintptr_t)d_dst) & 3u)) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     return bz_shift_bits(ctx, d_src, nbits, phase, d_dst);
+    BZ_API_CATCH
 }
 
 }  // extern "C"

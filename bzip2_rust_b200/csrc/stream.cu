@@ -130,7 +130,8 @@ static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, 
     cudaStream_t st = ctx->stream;
     if (out_cap < 16) return BZ2B200_E_CAP;
     if (ctx->timing) cudaEventRecord(ctx->ev_total[0], st);
-    BZ_CHECK(cudaMemsetAsync(d_out, 0, out_cap, st));
+    // the merge ORs bits into d_out: clear what this input can produce, not the caller's whole buffer
+    BZ_CHECK(cudaMemsetAsync(d_out, 0, std::min(out_cap, (bz2b200_compress_bound(n) + 64) & ~(size_t)3), st));
     u64 bitpos = whole_stream ? 32 : 0;
     u32 combined = 0;
     size_t pos = 0;
@@ -177,6 +178,7 @@ static int compress_core(bz2b200_ctx *ctx, const u8 *d_in, size_t n, int level, 
         hoff.resize(nb);
         u64 maxbits = 0;
         for (u32 k = 0; k < nb; k++) {
+            if (hbits[k] == ~0ull) { ctx->err = "huffman: packed block exceeds its slot"; return BZ2B200_E_CAP; }
             hoff[k] = bitpos;
             bitpos += hbits[k];
             maxbits = std::max(maxbits, hbits[k]);
@@ -229,7 +231,9 @@ size_t bz2b200_compress_bound(size_t n) {
 
 int bz2b200_compress_stream_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level, uint8_t *d_out,
                                 size_t out_cap, size_t *out_len) {
+    BZ_API_TRY
     if (!ctx || (!d_in && n) || !d_out || !out_len || level < 1 || level > 9) return BZ2B200_E_ARG;
+    if ((uintptr_t)d_out & 3u) return BZ2B200_E_ARG;            // the bit merge works on 32-bit words of d_out
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     u64 bits = 0;
@@ -237,10 +241,12 @@ int bz2b200_compress_stream_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n,
     if (rc) return rc;
     *out_len = (size_t)((bits + 7) / 8);
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 int bz2b200_compress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, uint8_t *out, size_t out_cap,
                             size_t *out_len) {
+    BZ_API_TRY
     if (!ctx || (!in && n) || !out || !out_len || level < 1 || level > 9) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -289,9 +295,11 @@ int bz2b200_compress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int l
     BZ_CHECK(cudaStreamSynchronize(ctx->s_down));
     *out_len = len;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 int bz2b200_crc32(bz2b200_ctx *ctx, const uint8_t *data, size_t n, uint32_t *crc) {
+    BZ_API_TRY
     if (!ctx || (!data && n) || !crc || n > 0xFFFFFF00u) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -303,10 +311,12 @@ int bz2b200_crc32(bz2b200_ctx *ctx, const uint8_t *data, size_t n, uint32_t *crc
     BZ_CHECK(cudaMemcpyAsync(crc, ctx->d_crc.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     BZ_CHECK(cudaStreamSynchronize(ctx->stream));
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 int bz2b200_rle1_split(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, uint8_t *rle1_out, size_t rle1_cap,
                        uint64_t *rle1_off, uint64_t *in_off, uint32_t *crc, uint32_t cap_blocks, uint32_t *nblocks) {
+    BZ_API_TRY
     if (!ctx || (!in && n) || !rle1_out || !rle1_off || !in_off || !crc || !nblocks || level < 1 || level > 9)
         return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -342,11 +352,13 @@ int bz2b200_rle1_split(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level,
     }
     *nblocks = total;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 // ---- multi-GPU sharding helpers -------------------------------------------------------------
 int bz2b200_stream_plan(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, uint64_t *block_start, uint32_t cap,
                         uint32_t *nblocks) {
+    BZ_API_TRY
     if (!ctx || (!in && n) || !block_start || !nblocks || level < 1 || level > 9) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -372,11 +384,13 @@ int bz2b200_stream_plan(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level
     block_start[total] = n;
     *nblocks = total;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 int bz2b200_compress_range(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int level, const uint64_t *block_start,
                            uint32_t nblocks_total, uint32_t first, uint32_t count, uint8_t *out, size_t out_cap,
                            uint64_t *out_bits, uint32_t *block_crcs) {
+    BZ_API_TRY
     if (!ctx || !in || !block_start || !out || !out_bits || !block_crcs || level < 1 || level > 9 ||
         first + count > nblocks_total)
         return BZ2B200_E_ARG;
@@ -406,12 +420,14 @@ int bz2b200_compress_range(bz2b200_ctx *ctx, const uint8_t *in, size_t n, int le
     memcpy(block_crcs, crcs.data(), (size_t)count * 4);
     *out_bits = bits;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 // Host-side ordered merge of bit strings (the writer thread of compress.rs:74-122 + bitwriter.rs:77-132).
 int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, const uint64_t *part_bits,
                           const uint32_t *const *part_crcs, const uint32_t *part_ncrc, uint8_t *out, size_t out_cap,
                           size_t *out_len) {
+    BZ_API_TRY
     if (level < 1 || level > 9 || nparts < 0 || !out || !out_len) return BZ2B200_E_ARG;
     u64 total = 32 + 80;
     for (int i = 0; i < nparts; i++) total += part_bits[i];
@@ -467,6 +483,7 @@ int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, con
     }
     *out_len = len;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 }  // extern "C"
@@ -474,6 +491,7 @@ int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, con
 // ---- device-resident variants of the sharding helpers (HBM-resident measurement at N > 1) --------------
 extern "C" int bz2b200_stream_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
                                        uint64_t *block_start, uint32_t cap, uint32_t *nblocks) {
+    BZ_API_TRY
     if (!ctx || (!d_in && n) || !block_start || !nblocks || level < 1 || level > 9) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
@@ -496,14 +514,16 @@ extern "C" int bz2b200_stream_plan_dev(bz2b200_ctx *ctx, const uint8_t *d_in, si
     block_start[total] = n;
     *nblocks = total;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }
 
 extern "C" int bz2b200_compress_range_dev(bz2b200_ctx *ctx, const uint8_t *d_in, size_t n, int level,
                                           const uint64_t *block_start, uint32_t nblocks_total, uint32_t first,
                                           uint32_t count, uint8_t *d_out, size_t out_cap, uint64_t *out_bits,
                                           uint32_t *block_crcs) {
+    BZ_API_TRY
     if (!ctx || !d_in || !block_start || !d_out || !out_bits || !block_crcs || level < 1 || level > 9 ||
-        first + count > nblocks_total)
+        first + count > nblocks_total || ((uintptr_t)d_out & 3u))
         return BZ2B200_E_ARG;
     *out_bits = 0;
     if (count == 0) return BZ2B200_OK;
@@ -521,4 +541,5 @@ extern "C" int bz2b200_compress_range_dev(bz2b200_ctx *ctx, const uint8_t *d_in,
     memcpy(block_crcs, crcs.data(), (size_t)count * 4);
     *out_bits = bits;
     return BZ2B200_OK;
+    BZ_API_CATCH
 }

@@ -13,7 +13,9 @@
  *     bz2b200_compress_stream uploads in chunks on its own stream while the first kernels
  *     run and downloads finished output on another; pass page-locked buffers for full
  *     overlap (pageable memory works, the copies then block).  _dev functions take DEVICE
- *     pointers on the context's GPU (used for HBM-resident measurement).
+ *     pointers on the context's GPU (used for HBM-resident measurement); device OUTPUT buffers
+ *     (d_out, d_dst) and the d_src of bz2b200_shift_bits_dev must be 4-byte aligned (the bit
+ *     merge works on 32-bit words): BZ2B200_E_ARG otherwise.
  *   - a context owns one GPU (streams, workspaces).  Calls on one context are serialised
  *     by an internal mutex; use one context per GPU for multi-GPU sharding.
  *   - there is no CPU fallback: if no CUDA device is usable, bz2b200_create fails.

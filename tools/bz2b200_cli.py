@@ -7,7 +7,10 @@ Only block size (-1..-9), mode (-z/-d/-t) and the file list change the output, e
 (compress.rs:50-55 reads only files[0] and block_size; this tool also accepts several files and stdin/stdout, which
 the reference advertises in its help text but does not implement, cli.rs:331-333).
 Compression writes FILE.bz2 (compress.rs:59-60); decompression strips ".bz2" (the reference appends ".txt", an
-author's test convenience, decompress.rs:67-70 -- not reproduced).  All work happens on the GPU through libbz2b200.
+author's test convenience, decompress.rs:67-70 -- not reproduced).  Input files are ALWAYS kept, as in the reference
+(cli.rs:314 "-k --keep ... ALWAYS KEEPS"; compress.rs never reads keep_input_files): -k is accepted and changes nothing.
+Decoding verifies every block CRC and the combined CRC (the reference only logs mismatches, decompress.rs:376-402) and
+accepts concatenated streams.  All work happens on the GPU through libbz2b200.
 """
 import argparse
 import os
@@ -26,12 +29,14 @@ def main(argv=None):
     ap.add_argument("-z", "--compress", dest="mode", action="store_const", const="z")
     ap.add_argument("-d", "--decompress", dest="mode", action="store_const", const="d")
     ap.add_argument("-t", "--test", dest="mode", action="store_const", const="t")
-    ap.add_argument("-k", "--keep", action="store_true", help="keep input files (the reference never deletes them)")
+    ap.add_argument("-k", "--keep", action="store_true", help="keep input files (always the case, as in the reference)")
     ap.add_argument("-f", "--force", action="store_true", help="overwrite existing output files")
     ap.add_argument("-c", "--stdout", action="store_true", help="write to standard output")
     ap.add_argument("-q", "--quiet", action="store_true")
     ap.add_argument("-v", "--verbose", action="count", default=0)
     ap.add_argument("-s", "--small", action="store_true", help="accepted and ignored (as in the reference)")
+    ap.add_argument("-L", "--license", action="store_true", help="display software version & license")
+    ap.add_argument("-V", "--version", action="store_true", help="display software version & license")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("files", nargs="*")
     a = ap.parse_args(argv)
@@ -39,6 +44,10 @@ def main(argv=None):
     mode = a.mode or "z"
 
     import bzip2_rust_b200 as bz
+    if a.license or a.version:
+        sys.stdout.write("bz2b200, a block-sorting file compressor on B200 GPUs.  %s\n"
+                         % bz.load_library().bz2b200_version().decode())
+        return 0
     eng = bz.Engine(a.device)
     rc = 0
     files = a.files or ["-"]
@@ -63,9 +72,7 @@ def main(argv=None):
                     rc = 1
                     continue
                 with open(oname, "wb") as f:
-                    f.write(out)
-                if not a.keep:
-                    os.unlink(name)
+                    f.write(out)                          # the input file stays (reference: "ALWAYS KEEPS")
             if a.verbose and not a.quiet:
                 sys.stderr.write("  %s: %d -> %d bytes (%.3f:1)\n" % (name, len(data), len(out),
                                                                      len(data) / max(1, len(out))))
