@@ -54,10 +54,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
+    path = os.environ.get("BZ2B200_LIB", SO_PATH)               # A/B builds of the same CUDA library (tools/ab_build.sh)
+    if not os.path.exists(path):
         raise ImportError("libbz2b200.so is missing: run `python -m bzip2_rust_b200.build` "
                           "(there is no CPU fallback)")
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(path)
     vp, u8p, u32p, u64p, szp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)
     L.bz2b200_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.bz2b200_destroy.argtypes = [vp]

@@ -38,7 +38,10 @@ __device__ __forceinline__ u32 padi(u32 i) { return i + (i >> 5); }   // conflic
 constexpr int RT_PAD = RT + RT / 32 + 1;
 
 // ---- local (shared memory) refinement: geometry ----
-constexpr int LW = 4096;                 // window capacity of k_refine_local (elements)
+#ifndef BZ_LW
+#define BZ_LW 3072
+#endif
+constexpr int LW = BZ_LW;               // window capacity of k_refine_local (elements)
 constexpr int LIPT = LW / BZ_THREADS;    // 16 per thread, blocked
 #ifndef BZ_LCAP
 #define BZ_LCAP 1024
@@ -46,10 +49,10 @@ constexpr int LIPT = LW / BZ_THREADS;    // 16 per thread, blocked
 constexpr int LCAP = BZ_LCAP;            // largest group that is refined locally
 constexpr int LTILE = LW - LCAP;         // nominal tile: a tile owns the groups that START inside it
 #ifndef BZ_SCAP
-#define BZ_SCAP 32
+#define BZ_SCAP 48
 #endif
 constexpr int SCAP = BZ_SCAP;            // groups up to this size are ranked by all-pairs counting
-static_assert(LCAP <= RT && LCAP * 2 <= LW && LCAP < (1 << 12), "local refinement geometry");
+static_assert(LW % BZ_THREADS == 0 && LW <= 4096 && LCAP <= RT && LCAP * 2 <= LW && LCAP <= (1 << 11) && SCAP < 64 && LW / (SCAP + 1) < 256, "local refinement geometry");
 constexpr int LWP = LW + LW / 32 + 1;    // padded u32 arrays (padi)
 __device__ __forceinline__ u32 padh(u32 i) { return i + 2u * (i >> 6); }   // u16 arrays, blocked access of 16
 constexpr int LWH = LW + 2 * (LW / 64) + 2;
@@ -461,18 +464,23 @@ __global__ void __launch_bounds__(BZ_THREADS, BZ_REFINE_MINB > 5 ? 5 : BZ_REFINE
 //      32-bit key with 3-4 stable LSD passes in shared memory (warp match ranking, as the global sweeps do)
 //   4. "still tied" flags by sorted position -> slots of the next list (exclusive scan + look-back over tiles),
 //      then SA rows, ranks and the next list are written once.
-constexpr size_t LOC_K_BYTES = ((size_t)LWP * 4 + 15) & ~(size_t)15;
+// shared memory of k_refine_local (dynamic, > 48 KB): K | IDXA | IDXB | GSE | UP | wh; the next-list staging reuses K..IDXB
+constexpr size_t LOC_K_BYTES = (size_t)LW * 4;
 constexpr size_t LOC_I_BYTES = ((size_t)LWH * 2 + 15) & ~(size_t)15;
-constexpr size_t LOC_U_BYTES = LW + 16;
-constexpr size_t LOC_SMEM = 2 * LOC_K_BYTES + 2 * LOC_I_BYTES + LOC_U_BYTES + 8 * 256 * 4;
+constexpr size_t LOC_G_BYTES = ((size_t)LWP * 4 + 15) & ~(size_t)15;
+constexpr size_t LOC_U_BYTES = ((size_t)LWH * 2 + 15) & ~(size_t)15;
+constexpr size_t LOC_SMEM = LOC_K_BYTES + 2 * LOC_I_BYTES + LOC_G_BYTES + LOC_U_BYTES + 8 * 256 * 4;
+static_assert(LOC_K_BYTES + 2 * LOC_I_BYTES >= (size_t)LW * 8, "staging area");
 __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u32 *err) {
     extern __shared__ __align__(16) u8 loc_smem[];
-    u32 *K = (u32 *)loc_smem;                                   // key2 | (medium group number << 20), by window index
-    u32 *HD = (u32 *)(loc_smem + LOC_K_BYTES);                  // group head rows by window index; later the sorted medium keys
-    u16 *IDXA = (u16 *)(loc_smem + 2 * LOC_K_BYTES);            // window indices of the medium entries (ping)
-    u16 *IDXB = (u16 *)(loc_smem + 2 * LOC_K_BYTES + LOC_I_BYTES);   // (pong); the buffer that is free at the end holds the slots
-    u8 *U = loc_smem + 2 * LOC_K_BYTES + 2 * LOC_I_BYTES;       // "still tied" by sorted window position
-    u32 *wh = (u32 *)(U + LOC_U_BYTES);
+    u32 *K = (u32 *)loc_smem;                                   // by window index: key2 << 12 | index; medium entries: group number << 20 | key2
+    u16 *IDXA = (u16 *)(loc_smem + LOC_K_BYTES);                // window indices of the medium entries (ping)
+    u16 *IDXB = (u16 *)(loc_smem + LOC_K_BYTES + LOC_I_BYTES);  // (pong)
+    u32 *GSE = (u32 *)(loc_smem + LOC_K_BYTES + 2 * LOC_I_BYTES);   // by window index (padded): group head row; then group start |
+                                                                // end << 16 (~0: not owned); then the result: position inside the
+                                                                // group | members with a smaller key2 << 11
+    u16 *UP = (u16 *)((u8 *)GSE + LOC_G_BYTES);                 // by SORTED window position (padded): window index | tied << 15
+    u32 *wh = (u32 *)((u8 *)UP + LOC_U_BYTES);                  // LSD counters; later the slots (u16) of the sorted positions
     __shared__ u16 MG_GS[LW / (SCAP + 1) + 4], MG_MB[LW / (SCAP + 1) + 4];
     __shared__ int wsi[8];
     __shared__ u32 wsu[8];
@@ -491,28 +499,28 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
     const u32 nom = min((u32)LTILE, cnt - base);                // ... of which the tile proper
     const int INF = 0x7fffffff;
     // ---- load (coalesced) ----
-#pragma unroll
+#pragma unroll 4
     for (int r = 0; r < LIPT; r++) {
         u32 i = r * BZ_THREADS + tid;
         if (i < wlen) {
             u64 x = __ldg(lin + i);
-            K[padi(i)] = (u32)(x >> FB) & (u32)FMASK;
-            HD[padi(i)] = (u32)(x >> (2 * FB));
+            K[i] = (((u32)(x >> FB) & (u32)FMASK) << 12) | i;        // unique inside the window: key2, then window index
+            GSE[padi(i)] = (u32)(x >> (2 * FB));
         }
+        UP[padh(i)] = 0xffffu;
     }
-    for (int i = tid; i < (LW + 16) / 4; i += BZ_THREADS) ((u32 *)U)[i] = 0;
     if (tid == 0) s_prevhead = base > 0 ? (u32)(__ldg(lin - 1) >> (2 * FB)) : 0xffffffffu;
     __syncthreads();
-    // ---- 1. group extents ----
+    // ---- 1. group extents (blocked: thread owns entries [16 tid, 16 tid + 16)) ----
     const u32 eb = tid * LIPT;
     u32 gfm = 0;                                                // bit r: entry eb + r starts a group
     {
-        u32 prev = tid == 0 ? s_prevhead : HD[padi(eb - 1)];
-#pragma unroll
+        u32 prev = tid == 0 ? s_prevhead : GSE[padi(eb - 1)];
+#pragma unroll 4
         for (int r = 0; r < LIPT; r++) {
             u32 i = eb + r;
             if (i < wlen) {
-                u32 hc = HD[padi(i)];
+                u32 hc = GSE[padi(i)];
                 if (hc != prev) gfm |= 1u << r;
                 prev = hc;
             }
@@ -522,47 +530,70 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
     const int gin = block_excl_max(gfm ? (int)(eb + 31 - __clz(gfm)) : -1, wsi, dummy);      // last group start before my entries
     int nout = block_excl_min_rev(gfm ? (int)(eb + __ffs(gfm) - 1) : INF, wsi, dummy);       // first group start after them
     if (nout == INF) nout = (int)wlen;
-    // gse[r] = group start | group end << 16 of an OWNED entry (the group starts inside the tile proper), else ~0
-    u32 gse[LIPT];
-    u32 mcount = 0, mstarts = 0;
-#pragma unroll
+    // an entry is OWNED when its group starts inside the tile proper; medium = owned, more than SCAP members
+    u32 mcount = 0, mstarts = 0, medmask = 0;
+#pragma unroll 2
     for (int r = 0; r < LIPT; r++) {
         u32 i = eb + r;
-        gse[r] = 0xffffffffu;
         if (i < wlen) {
             u32 below = gfm & ((2u << r) - 1u);
             int gs = below ? (int)(eb + 31 - __clz(below)) : gin;
-            u32 above = r == LIPT - 1 ? 0u : gfm >> (r + 1);
+            u32 above = gfm >> (r + 1);
             int ge = above ? (int)(eb + r + __ffs(above)) : nout;
+            u32 v = 0xffffffffu;
             if (gs >= 0 && gs < (int)nom) {
-                gse[r] = (u32)gs | ((u32)ge << 16);
+                v = (u32)gs | ((u32)ge << 16);
                 u32 size = (u32)(ge - gs);
                 if (size > (u32)LCAP) atomicOr(err, 1u);         // cannot happen: LOC groups are at most LCAP long
-                if (size > (u32)SCAP) { mcount++; if ((u32)gs == i) mstarts++; }
+                if (size > (u32)SCAP) { medmask |= 1u << r; mcount++; if ((u32)gs == i) mstarts++; }
             }
+            GSE[padi(i)] = v;                                   // the head rows are not needed any more (all flags are computed)
         }
     }
     u32 mtot;
     const u32 mex = block_excl_sum(mcount | (mstarts << 16), wsu, mtot);
     const u32 M = mtot & 0xffffu, nmg = mtot >> 16;
-    {
+    if (medmask) {
         u32 midx = mex & 0xffffu;
         u32 mgnext = mex >> 16;                                 // number of the next medium group to start
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < LIPT; r++) {
-            if (gse[r] != 0xffffffffu) {
-                u32 i = eb + r, gs = gse[r] & 0xffffu, ge = gse[r] >> 16;
-                if (ge - gs > (u32)SCAP) {
-                    if (gs == i) { MG_GS[mgnext] = (u16)gs; MG_MB[mgnext] = (u16)midx; mgnext++; }
-                    K[padi(i)] |= (mgnext - 1u) << FB;          // the group of this entry is the last one that started
-                    IDXA[padh(midx)] = (u16)i;
-                    midx++;
-                }
+            if ((medmask >> r) & 1u) {
+                u32 i = eb + r;
+                if ((gfm >> r) & 1u) { MG_GS[mgnext] = (u16)i; MG_MB[mgnext] = (u16)midx; mgnext++; }
+                K[i] = ((mgnext - 1u) << FB) | (K[i] >> 12);    // the group of this entry is the last one that started
+                IDXA[padh(midx)] = (u16)i;
+                midx++;
             }
         }
     }
     __syncthreads();
-    // ---- 3. medium groups: LSD sort of the window indices by (group number | key2) ----
+    // ---- 2. small groups: all-pairs, entry i = r * 256 + tid (neighbouring lanes sit in the same or adjacent groups, so a
+    //         warp's loop count is the largest group among 32 consecutive entries and the key reads are broadcasts) ----
+#pragma unroll 1
+    for (int r = 0; r < LIPT; r++) {
+        u32 i = r * BZ_THREADS + tid;
+        if (i < wlen) {
+            u32 g = GSE[padi(i)];
+            u32 gs = g & 0xffffu, ge = g >> 16;
+            if (g != 0xffffffffu && ge - gs <= (u32)SCAP) {
+                // keys are unique (index in the low bits): three counts give the position inside the group, the start of
+                // the subgroup (members with a smaller key2) and the number of members with the same key2
+                const u32 mine = K[i], lo = mine & ~0xfffu, up = lo + 0x1000u;
+                u32 off = 0, lt = 0, le = 0;
+#pragma unroll 4
+                for (u32 q = gs; q < ge; q++) {
+                    u32 k = K[q];
+                    off += k < mine;
+                    lt += k < lo;
+                    le += k < up;
+                }
+                GSE[padi(i)] = off | (lt << 11);
+                UP[padh(gs + off)] = (u16)(i | ((le - lt > 1u) ? 0x8000u : 0u));
+            }
+        }
+    }
+    // ---- 3. medium groups: stable LSD sort of the window indices by (group number | key2), 8 bits per pass ----
     u16 *src = IDXA, *dst = IDXB;
     if (M) {
         const int gb = nmg > 1 ? 32 - __clz((int)nmg - 1) : 0;
@@ -570,31 +601,24 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
         const u32 C = ((M + BZ_THREADS - 1) / BZ_THREADS) * 32;  // entries per warp, a multiple of 32
         const u32 lt = (1u << lane) - 1u;
         u32 *whw = wh + w * 256;
+        const u32 j0 = (u32)w * C + lane;
+#pragma unroll 1
         for (int p = 0; p < passes; p++) {
             const int shift = 8 * p;
 #pragma unroll
             for (int k = 0; k < 8; k++) wh[k * 256 + tid] = 0;
             __syncthreads();
-            u32 tmp[LIPT];
-#pragma unroll
-            for (int rr = 0; rr < LIPT; rr++) {
-                tmp[rr] = 0xffffffffu;
-                if ((u32)rr * 32u < C) {                        // warp uniform
-                    u32 j = (u32)w * C + rr * 32 + lane;
-                    bool valid = j < M;
-                    u32 idx = valid ? (u32)src[padh(j)] : 0u;
-                    u32 d = valid ? (K[padi(idx)] >> shift) & 255u : 256u + (u32)lane;
-                    u32 peers = __match_any_sync(0xffffffffu, d);
-                    u32 before = __popc(peers & lt);
-                    u32 old = 0;
-                    if (before == 0 && valid) { old = whw[d]; whw[d] = old + __popc(peers); }
-                    old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-                    if (valid) tmp[rr] = idx | ((old + before) << 12) | (d << 24);
-                    __syncwarp();
-                }
+#pragma unroll 1
+            for (u32 o = 0; o < C; o += 32) {                   // digit counts of this warp's entries
+                u32 j = j0 + o;
+                bool valid = j < M;
+                u32 d = valid ? (K[src[padh(j)]] >> shift) & 255u : 256u + (u32)lane;
+                u32 peers = __match_any_sync(0xffffffffu, d);
+                if (valid && (peers & lt) == 0) whw[d] += __popc(peers);
+                __syncwarp();
             }
             __syncthreads();
-            {
+            {   // digit = tid: exclusive bases, digit major, then warp
                 u32 c[8], total = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) { c[k] = wh[k * 256 + tid]; total += c[k]; }
@@ -604,95 +628,78 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
                 for (int k = 0; k < 8; k++) { wh[k * 256 + tid] = run; run += c[k]; }
             }
             __syncthreads();
-#pragma unroll
-            for (int rr = 0; rr < LIPT; rr++) {
-                if (tmp[rr] != 0xffffffffu) {
-                    u32 idx = tmp[rr] & 0xfffu, rk = (tmp[rr] >> 12) & 0xfffu, d = tmp[rr] >> 24;
-                    dst[padh(whw[d] + rk)] = (u16)idx;
-                }
+#pragma unroll 1
+            for (u32 o = 0; o < C; o += 32) {                   // stable ranks, scatter
+                u32 j = j0 + o;
+                bool valid = j < M;
+                u32 idx = valid ? (u32)src[padh(j)] : 0u;
+                u32 d = valid ? (K[idx] >> shift) & 255u : 256u + (u32)lane;
+                u32 peers = __match_any_sync(0xffffffffu, d);
+                u32 before = __popc(peers & lt);
+                u32 old = 0;
+                if (before == 0 && valid) { old = whw[d]; whw[d] = old + __popc(peers); }
+                old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+                if (valid) dst[padh(old + before)] = (u16)idx;
+                __syncwarp();
             }
             __syncthreads();
             u16 *sw = src; src = dst; dst = sw;
         }
-        for (u32 j = tid; j < M; j += BZ_THREADS) HD[padi(j)] = K[padi(src[padh(j)])];     // keys in sorted order
-        __syncthreads();
-    }
-    // mres[r]: sorted entry eb + r of the medium array: window position | subgroup start position << 12 | tied << 24
-    u32 mres[LIPT];
-#pragma unroll
-    for (int r = 0; r < LIPT; r++) mres[r] = 0xffffffffu;
-    if (M) {
+        // subgroups of the sorted medium entries (blocked: thread owns sorted entries [16 tid, 16 tid + 16))
         u32 sfm = 0;                                            // bit r: sorted entry eb + r starts a subgroup; bit 16: entry eb + 16
         if (eb < M) {
-            u32 prev = eb == 0 ? 0xffffffffu : HD[padi(eb - 1)];    // ~0 is no key: group numbers stay below 2^12
-#pragma unroll
+            u32 prev = eb == 0 ? 0xffffffffu : K[src[padh(eb - 1)]];    // ~0 is no key: group numbers stay below 2^12
+#pragma unroll 4
             for (int r = 0; r <= LIPT; r++) {
                 u32 j = eb + r;
                 if (j < M) {
-                    u32 ck = HD[padi(j)];
+                    u32 ck = K[src[padh(j)]];
                     if (ck != prev) sfm |= 1u << r;
                     prev = ck;
                 } else sfm |= 1u << r;                          // past the end: a boundary
             }
         }
-        u32 own = sfm & 0xffffu;
+        const u32 own = sfm & 0xffffu;
         const int jin = block_excl_max((eb < M && own) ? (int)(eb + 31 - __clz(own)) : -1, wsi, dummy);
         if (eb < M) {
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < LIPT; r++) {
                 u32 j = eb + r;
                 if (j < M) {
                     u32 below = own & ((2u << r) - 1u);
                     u32 js = below ? eb + 31 - __clz(below) : (u32)jin;
-                    u32 g = HD[padi(j)] >> FB;
-                    u32 gs = MG_GS[g], mb = MG_MB[g];
-                    u32 pos = gs + (j - mb), sub = gs + (js - mb);
-                    u32 tied = (((sfm >> r) & 1u) && ((sfm >> (r + 1)) & 1u)) ? 0u : 1u;
-                    mres[r] = pos | (sub << 12) | (tied << 24);
-                    U[pos] = (u8)tied;
+                    u32 i = src[padh(j)];
+                    u32 g = K[i] >> FB;
+                    u32 mb = MG_MB[g];
+                    u32 tied = (((sfm >> r) & 1u) && ((sfm >> (r + 1)) & 1u)) ? 0u : 0x8000u;
+                    GSE[padi(i)] = (j - mb) | ((js - mb) << 11);     // position in the group | members with a smaller key2
+                    UP[padh(MG_GS[g] + (j - mb))] = (u16)(i | tied);
                 }
-            }
-        }
-    }
-    // ---- 2. small groups: all-pairs ----
-    u32 res[LIPT];                                              // by window entry: position | subgroup start << 12 | tied << 24
-#pragma unroll
-    for (int r = 0; r < LIPT; r++) {
-        res[r] = 0xffffffffu;
-        if (gse[r] != 0xffffffffu) {
-            u32 i = eb + r, gs = gse[r] & 0xffffu, ge = gse[r] >> 16;
-            if (ge - gs <= (u32)SCAP) {
-                u32 mine = K[padi(i)];
-                u32 lt = 0, eq = 0, eqb = 0;
-                for (u32 q = gs; q < ge; q++) {
-                    u32 k = K[padi(q)];
-                    lt += k < mine;
-                    u32 e = k == mine;
-                    eq += e;
-                    eqb += e & (u32)(q < i);
-                }
-                u32 pos = gs + lt + eqb, tied = eq > 1u;
-                res[r] = pos | ((gs + lt) << 12) | (tied << 24);
-                U[pos] = (u8)tied;
             }
         }
     }
     __syncthreads();
-    // ---- 4. slots of the next list ----
+    // ---- 4. slots of the next list: exclusive count of the tied entries by sorted position ----
     u32 tu;
+    u16 *slot = (u16 *)wh;
     {
-        uint4 q = *(const uint4 *)(U + eb);
-        u32 wd[4] = {q.x, q.y, q.z, q.w};
-        u32 c = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) c += __popc(wd[k]);          // the bytes are 0 or 1
-        u32 run = block_excl_sum(c, wsu, tu);
-#pragma unroll
+        u32 tm = 0;
+#pragma unroll 4
         for (int r = 0; r < LIPT; r++) {
-            dst[padh(eb + r)] = (u16)run;
-            run += (wd[r >> 2] >> (8 * (r & 3))) & 1u;
+            u32 e = UP[padh(eb + r)];
+            if (e != 0xffffu && (e & 0x8000u)) tm |= 1u << r;
+        }
+        u32 run = block_excl_sum((u32)__popc(tm), wsu, tu);
+#pragma unroll 4
+        for (int r = 0; r < LIPT; r++) {
+            slot[eb + r] = (u16)run;
+            run += (tm >> r) & 1u;
         }
     }
+    __syncthreads();
+    // ---- write SA rows and ranks, by sorted position (the rows of a group are consecutive); entries that stay tied
+    //      are staged in slot order.  Warp 0 first obtains this tile's offset in the next list: it waits for the tiles
+    //      before it while the other warps are busy with their stores. ----
     if (tid < 32) {
         Tri agg; agg.a = -1; agg.b = -1; agg.c = tu;
         Tri ex = tile_lookback(a.tstate + (size_t)b * a.rtiles, t, agg);
@@ -701,40 +708,26 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
             if (base + LTILE >= cnt) a.cnt_out[b] = (a.depth_after >= a.len[b]) ? 0u : ex.c + tu;
         }
     }
-    __syncthreads();
-    // ---- write SA rows, ranks, next list ----
+    u64 *stg = (u64 *)loc_smem;                                  // [tu] next-list entries in slot order (K, IDXA, IDXB are free)
     u32 *sa = a.SA + ob, *rank = a.RANK + ob;
-    u64 *lout = a.LOUT + ob + s_ex.c;
-#pragma unroll
+#pragma unroll 2
     for (int r = 0; r < LIPT; r++) {
-        if (res[r] != 0xffffffffu) {
-            u64 x = __ldg(lin + eb + r);
+        u32 pos = r * BZ_THREADS + tid;
+        u32 e = UP[padh(pos)];
+        if (e != 0xffffu) {
+            u32 i = e & 0xfffu;
+            u32 rr = GSE[padi(i)];
+            u64 x = __ldg(lin + i);
             u32 head = (u32)(x >> (2 * FB)), s = (u32)(x & FMASK);
-            u32 gs = gse[r] & 0xffffu;
-            u32 pos = res[r] & 0xfffu, sub = (res[r] >> 12) & 0xfffu;
-            u32 nh = head + (sub - gs);
-            sa[head + (pos - gs)] = s;
+            u32 nh = head + (rr >> 11);
+            sa[head + (rr & 0x7ffu)] = s;
             rank[s] = nh;
-            if (res[r] >> 24) lout[dst[padh(pos)]] = ((u64)nh << (2 * FB)) | s;
+            if (e & 0x8000u) stg[slot[pos]] = ((u64)nh << (2 * FB)) | s;
         }
     }
-    if (M && eb < M) {
-#pragma unroll
-        for (int r = 0; r < LIPT; r++) {
-            if (mres[r] != 0xffffffffu) {
-                u32 j = eb + r;
-                u32 i = src[padh(j)];
-                u64 x = __ldg(lin + i);
-                u32 head = (u32)(x >> (2 * FB)), s = (u32)(x & FMASK);
-                u32 gs = MG_GS[HD[padi(j)] >> FB];
-                u32 pos = mres[r] & 0xfffu, sub = (mres[r] >> 12) & 0xfffu;
-                u32 nh = head + (sub - gs);
-                sa[head + (pos - gs)] = s;
-                rank[s] = nh;
-                if (mres[r] >> 24) lout[dst[padh(pos)]] = ((u64)nh << (2 * FB)) | s;
-            }
-        }
-    }
+    __syncthreads();
+    u64 *lout = a.LOUT + ob + s_ex.c;
+    for (u32 q = tid; q < tu; q += BZ_THREADS) lout[q] = stg[q];
 }
 
 // Path selector of the reference (bwt_sort.rs:29, lms_complexity sais_fallback.rs:821-829, LMS typing :59-131): a block
