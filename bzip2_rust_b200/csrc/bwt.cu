@@ -49,10 +49,10 @@ constexpr int LIPT = LW / BZ_THREADS;    // 16 per thread, blocked
 constexpr int LCAP = BZ_LCAP;            // largest group that is refined locally
 constexpr int LTILE = LW - LCAP;         // nominal tile: a tile owns the groups that START inside it
 #ifndef BZ_SCAP
-#define BZ_SCAP 48
+#define BZ_SCAP 128
 #endif
 constexpr int SCAP = BZ_SCAP;            // groups up to this size are ranked by all-pairs counting
-static_assert(LW % BZ_THREADS == 0 && LW <= 4096 && LCAP <= RT && LCAP * 2 <= LW && LCAP <= (1 << 11) && SCAP < 64 && LW / (SCAP + 1) < 256, "local refinement geometry");
+static_assert(LW % BZ_THREADS == 0 && LW <= 4096 && LCAP <= RT && LCAP * 2 <= LW && LCAP <= (1 << 11) && SCAP < LCAP && LW / (SCAP + 1) < 256, "local refinement geometry");
 constexpr int LWP = LW + LW / 32 + 1;    // padded u32 arrays (padi)
 __device__ __forceinline__ u32 padh(u32 i) { return i + 2u * (i >> 6); }   // u16 arrays, blocked access of 16
 constexpr int LWH = LW + 2 * (LW / 64) + 2;
@@ -469,18 +469,20 @@ constexpr size_t LOC_K_BYTES = (size_t)LW * 4;
 constexpr size_t LOC_I_BYTES = ((size_t)LWH * 2 + 15) & ~(size_t)15;
 constexpr size_t LOC_G_BYTES = ((size_t)LWP * 4 + 15) & ~(size_t)15;
 constexpr size_t LOC_U_BYTES = ((size_t)LWH * 2 + 15) & ~(size_t)15;
-constexpr size_t LOC_SMEM = LOC_K_BYTES + 2 * LOC_I_BYTES + LOC_G_BYTES + LOC_U_BYTES + 8 * 256 * 4;
+constexpr size_t LOC_W_BYTES = (size_t)(LW * 4 > 8 * 256 * 4 ? LW * 4 : 8 * 256 * 4);
+constexpr size_t LOC_SMEM = LOC_K_BYTES + 2 * LOC_I_BYTES + LOC_G_BYTES + LOC_U_BYTES + LOC_W_BYTES;
 static_assert(LOC_K_BYTES + 2 * LOC_I_BYTES >= (size_t)LW * 8, "staging area");
-__global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u32 *err) {
+#ifndef BZ_LOCAL_MINB
+#define BZ_LOCAL_MINB 3
+#endif
+__global__ void __launch_bounds__(BZ_THREADS, BZ_LOCAL_MINB) k_refine_local(RefineArgs a, u32 *err) {
     extern __shared__ __align__(16) u8 loc_smem[];
-    u32 *K = (u32 *)loc_smem;                                   // by window index: key2 << 12 | index; medium entries: group number << 20 | key2
+    u32 *K = (u32 *)loc_smem;                                   // by window index: key2 << 12 | index (unique); medium entries: group number << 20 | key2
     u16 *IDXA = (u16 *)(loc_smem + LOC_K_BYTES);                // window indices of the medium entries (ping)
     u16 *IDXB = (u16 *)(loc_smem + LOC_K_BYTES + LOC_I_BYTES);  // (pong)
-    u32 *GSE = (u32 *)(loc_smem + LOC_K_BYTES + 2 * LOC_I_BYTES);   // by window index (padded): group head row; then group start |
-                                                                // end << 16 (~0: not owned); then the result: position inside the
-                                                                // group | members with a smaller key2 << 11
-    u16 *UP = (u16 *)((u8 *)GSE + LOC_G_BYTES);                 // by SORTED window position (padded): window index | tied << 15
-    u32 *wh = (u32 *)((u8 *)UP + LOC_U_BYTES);                  // LSD counters; later the slots (u16) of the sorted positions
+    u32 *GSE = (u32 *)(loc_smem + LOC_K_BYTES + 2 * LOC_I_BYTES);   // by window index (padded): group head row; then group start | end << 16 (~0: not owned)
+    u16 *UP = (u16 *)((u8 *)GSE + LOC_G_BYTES);                 // by SORTED window position (padded): window index of the entry (0xffff: none)
+    u32 *wh = (u32 *)((u8 *)UP + LOC_U_BYTES);                  // LSD counters; later, by sorted position: slot | distance to the subgroup start << 12 | tied << 31
     __shared__ u16 MG_GS[LW / (SCAP + 1) + 4], MG_MB[LW / (SCAP + 1) + 4];
     __shared__ int wsi[8];
     __shared__ u32 wsu[8];
@@ -504,14 +506,14 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
         u32 i = r * BZ_THREADS + tid;
         if (i < wlen) {
             u64 x = __ldg(lin + i);
-            K[i] = (((u32)(x >> FB) & (u32)FMASK) << 12) | i;        // unique inside the window: key2, then window index
+            K[i] = (((u32)(x >> FB) & (u32)FMASK) << 12) | i;
             GSE[padi(i)] = (u32)(x >> (2 * FB));
         }
         UP[padh(i)] = 0xffffu;
     }
     if (tid == 0) s_prevhead = base > 0 ? (u32)(__ldg(lin - 1) >> (2 * FB)) : 0xffffffffu;
     __syncthreads();
-    // ---- 1. group extents (blocked: thread owns entries [16 tid, 16 tid + 16)) ----
+    // ---- 1. group extents (blocked: thread owns entries [IPT tid, IPT tid + IPT)) ----
     const u32 eb = tid * LIPT;
     u32 gfm = 0;                                                // bit r: entry eb + r starts a group
     {
@@ -532,22 +534,29 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
     if (nout == INF) nout = (int)wlen;
     // an entry is OWNED when its group starts inside the tile proper; medium = owned, more than SCAP members
     u32 mcount = 0, mstarts = 0, medmask = 0;
-#pragma unroll 2
-    for (int r = 0; r < LIPT; r++) {
-        u32 i = eb + r;
-        if (i < wlen) {
-            u32 below = gfm & ((2u << r) - 1u);
-            int gs = below ? (int)(eb + 31 - __clz(below)) : gin;
-            u32 above = gfm >> (r + 1);
-            int ge = above ? (int)(eb + r + __ffs(above)) : nout;
-            u32 v = 0xffffffffu;
-            if (gs >= 0 && gs < (int)nom) {
-                v = (u32)gs | ((u32)ge << 16);
-                u32 size = (u32)(ge - gs);
-                if (size > (u32)LCAP) atomicOr(err, 1u);         // cannot happen: LOC groups are at most LCAP long
-                if (size > (u32)SCAP) { medmask |= 1u << r; mcount++; if ((u32)gs == i) mstarts++; }
+    {
+        int ge = nout;                                          // backwards: the end of the group of entry eb + r
+        u32 gem[LIPT];
+#pragma unroll
+        for (int r = LIPT - 1; r >= 0; r--) {
+            gem[r] = (u32)ge;
+            if ((gfm >> r) & 1u) ge = (int)(eb + r);
+        }
+        int gs = gin;
+#pragma unroll
+        for (int r = 0; r < LIPT; r++) {
+            u32 i = eb + r;
+            if ((gfm >> r) & 1u) gs = (int)i;
+            if (i < wlen) {
+                u32 v = 0xffffffffu;
+                if (gs >= 0 && gs < (int)nom) {
+                    v = (u32)gs | (gem[r] << 16);
+                    u32 size = gem[r] - (u32)gs;
+                    if (size > (u32)LCAP) atomicOr(err, 1u);     // cannot happen: LOC groups are at most LCAP long
+                    if (size > (u32)SCAP) { medmask |= 1u << r; mcount++; if ((u32)gs == i) mstarts++; }
+                }
+                GSE[padi(i)] = v;                               // the head rows are not needed any more (all flags are computed)
             }
-            GSE[padi(i)] = v;                                   // the head rows are not needed any more (all flags are computed)
         }
     }
     u32 mtot;
@@ -569,7 +578,8 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
     }
     __syncthreads();
     // ---- 2. small groups: all-pairs, entry i = r * 256 + tid (neighbouring lanes sit in the same or adjacent groups, so a
-    //         warp's loop count is the largest group among 32 consecutive entries and the key reads are broadcasts) ----
+    //         warp's loop count is the largest group among 32 consecutive entries and the key reads are broadcasts).
+    //         Keys are unique (index in the low bits): the members with a smaller key give the sorted position. ----
 #pragma unroll 1
     for (int r = 0; r < LIPT; r++) {
         u32 i = r * BZ_THREADS + tid;
@@ -577,25 +587,17 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
             u32 g = GSE[padi(i)];
             u32 gs = g & 0xffffu, ge = g >> 16;
             if (g != 0xffffffffu && ge - gs <= (u32)SCAP) {
-                // keys are unique (index in the low bits): three counts give the position inside the group, the start of
-                // the subgroup (members with a smaller key2) and the number of members with the same key2
-                const u32 mine = K[i], lo = mine & ~0xfffu, up = lo + 0x1000u;
-                u32 off = 0, lt = 0, le = 0;
+                const u32 mine = K[i];
+                u32 off = 0;
 #pragma unroll 4
-                for (u32 q = gs; q < ge; q++) {
-                    u32 k = K[q];
-                    off += k < mine;
-                    lt += k < lo;
-                    le += k < up;
-                }
-                GSE[padi(i)] = off | (lt << 11);
-                UP[padh(gs + off)] = (u16)(i | ((le - lt > 1u) ? 0x8000u : 0u));
+                for (u32 q = gs; q < ge; q++) off += K[q] < mine;
+                UP[padh(gs + off)] = (u16)i;
             }
         }
     }
     // ---- 3. medium groups: stable LSD sort of the window indices by (group number | key2), 8 bits per pass ----
-    u16 *src = IDXA, *dst = IDXB;
     if (M) {
+        u16 *src = IDXA, *dst = IDXB;
         const int gb = nmg > 1 ? 32 - __clz((int)nmg - 1) : 0;
         const int passes = (FB + gb + 7) / 8;
         const u32 C = ((M + BZ_THREADS - 1) / BZ_THREADS) * 32;  // entries per warp, a multiple of 32
@@ -645,54 +647,46 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
             __syncthreads();
             u16 *sw = src; src = dst; dst = sw;
         }
-        // subgroups of the sorted medium entries (blocked: thread owns sorted entries [16 tid, 16 tid + 16))
-        u32 sfm = 0;                                            // bit r: sorted entry eb + r starts a subgroup; bit 16: entry eb + 16
-        if (eb < M) {
-            u32 prev = eb == 0 ? 0xffffffffu : K[src[padh(eb - 1)]];    // ~0 is no key: group numbers stay below 2^12
-#pragma unroll 4
-            for (int r = 0; r <= LIPT; r++) {
-                u32 j = eb + r;
-                if (j < M) {
-                    u32 ck = K[src[padh(j)]];
-                    if (ck != prev) sfm |= 1u << r;
-                    prev = ck;
-                } else sfm |= 1u << r;                          // past the end: a boundary
-            }
-        }
-        const u32 own = sfm & 0xffffu;
-        const int jin = block_excl_max((eb < M && own) ? (int)(eb + 31 - __clz(own)) : -1, wsi, dummy);
-        if (eb < M) {
-#pragma unroll 1
-            for (int r = 0; r < LIPT; r++) {
-                u32 j = eb + r;
-                if (j < M) {
-                    u32 below = own & ((2u << r) - 1u);
-                    u32 js = below ? eb + 31 - __clz(below) : (u32)jin;
-                    u32 i = src[padh(j)];
-                    u32 g = K[i] >> FB;
-                    u32 mb = MG_MB[g];
-                    u32 tied = (((sfm >> r) & 1u) && ((sfm >> (r + 1)) & 1u)) ? 0u : 0x8000u;
-                    GSE[padi(i)] = (j - mb) | ((js - mb) << 11);     // position in the group | members with a smaller key2
-                    UP[padh(MG_GS[g] + (j - mb))] = (u16)(i | tied);
-                }
-            }
+        for (u32 j = tid; j < M; j += BZ_THREADS) {             // sorted medium entry j -> its window position
+            u32 i = src[padh(j)];
+            u32 g = K[i] >> FB;
+            UP[padh((u32)MG_GS[g] + (j - (u32)MG_MB[g]))] = (u16)i;
         }
     }
     __syncthreads();
-    // ---- 4. slots of the next list: exclusive count of the tied entries by sorted position ----
+    // ---- 4. subgroups and slots, by sorted position (blocked): position p starts a subgroup when it starts a group or
+    //         its key2 differs from the one before; entries of subgroups with more than one member stay tied ----
     u32 tu;
-    u16 *slot = (u16 *)wh;
     {
-        u32 tm = 0;
-#pragma unroll 4
-        for (int r = 0; r < LIPT; r++) {
-            u32 e = UP[padh(eb + r)];
-            if (e != 0xffffu && (e & 0x8000u)) tm |= 1u << r;
+        u32 sfm = 0;                                            // bit r: position eb + r starts a subgroup (or holds nothing); bit IPT: position eb + IPT
+        u32 occ = 0;                                            // bit r: position eb + r holds an entry
+        u32 pk = 0xffffffffu;                                   // key2 of position eb - 1 (only compared inside a group)
+        if (eb > 0) {
+            u32 e = UP[padh(eb - 1)];
+            if (e != 0xffffu) { u32 g = GSE[padi(e)]; pk = (g >> 16) - (g & 0xffffu) > (u32)SCAP ? K[e] & (u32)FMASK : K[e] >> 12; }
         }
+#pragma unroll 2
+        for (int r = 0; r <= LIPT; r++) {
+            u32 p = eb + r;
+            u32 e = p < (u32)LW ? (u32)UP[padh(p)] : 0xffffu;
+            if (e == 0xffffu) { sfm |= 1u << r; pk = 0xffffffffu; continue; }
+            u32 g = GSE[padi(e)];
+            u32 k2 = (g >> 16) - (g & 0xffffu) > (u32)SCAP ? K[e] & (u32)FMASK : K[e] >> 12;
+            if (p == (g & 0xffffu) || k2 != pk) sfm |= 1u << r;
+            pk = k2;
+            occ |= 1u << r;
+        }
+        occ &= (1u << LIPT) - 1u;
+        const u32 own = sfm & ((1u << LIPT) - 1u);
+        const u32 tm = occ & ~(own & (sfm >> 1));               // tied: not (subgroup start and the next position starts one)
+        const int pin = block_excl_max(own ? (int)(eb + 31 - __clz(own)) : -1, wsi, dummy);   // last subgroup start before my positions
         u32 run = block_excl_sum((u32)__popc(tm), wsu, tu);
+        int ps = pin;
 #pragma unroll 4
         for (int r = 0; r < LIPT; r++) {
-            slot[eb + r] = (u16)run;
+            u32 p = eb + r;
+            if ((own >> r) & 1u) ps = (int)p;
+            wh[p] = run | ((p - (u32)ps) << 12) | (((tm >> r) & 1u) << 31);
             run += (tm >> r) & 1u;
         }
     }
@@ -712,17 +706,18 @@ __global__ void __launch_bounds__(BZ_THREADS, 3) k_refine_local(RefineArgs a, u3
     u32 *sa = a.SA + ob, *rank = a.RANK + ob;
 #pragma unroll 2
     for (int r = 0; r < LIPT; r++) {
-        u32 pos = r * BZ_THREADS + tid;
-        u32 e = UP[padh(pos)];
+        u32 p = r * BZ_THREADS + tid;
+        u32 e = UP[padh(p)];
         if (e != 0xffffu) {
-            u32 i = e & 0xfffu;
-            u32 rr = GSE[padi(i)];
-            u64 x = __ldg(lin + i);
+            u32 gs = GSE[padi(e)] & 0xffffu;
+            u32 v = wh[p];
+            u64 x = __ldg(lin + e);
             u32 head = (u32)(x >> (2 * FB)), s = (u32)(x & FMASK);
-            u32 nh = head + (rr >> 11);
-            sa[head + (rr & 0x7ffu)] = s;
+            u32 off = p - gs;                                   // position inside the group
+            u32 nh = head + off - ((v >> 12) & 0x7ffffu);       // row of the first member of the subgroup = new rank
+            sa[head + off] = s;
             rank[s] = nh;
-            if (e & 0x8000u) stg[slot[pos]] = ((u64)nh << (2 * FB)) | s;
+            if (v >> 31) stg[v & 0xfffu] = ((u64)nh << (2 * FB)) | s;
         }
     }
     __syncthreads();
