@@ -37,6 +37,8 @@ EXPORTS = [
     "bz2b200_set_timing", "bz2b200_get_timing", "bz2b200_get_bwt_stats", "bz2b200_kernel_stats",
     "bz2b200_reset_kernel_stats", "bz2b200_stream_plan_dev", "bz2b200_compress_range_dev",
     "bz2b200_shard_plan_dev", "bz2b200_shard_compress_dev", "bz2b200_shift_bits_dev", "bz2b200_shard_scan_dev",
+    "bz2b200_create_multi", "bz2b200_destroy_multi", "bz2b200_last_error_multi", "bz2b200_multi_devices",
+    "bz2b200_multi_context", "bz2b200_compress_stream_multi", "bz2b200_multi_stats",
 ]
 
 
@@ -102,6 +104,16 @@ def load_library():
                                        C.POINTER(C.c_uint64)]
     L.bz2b200_reset_kernel_stats.argtypes = [vp]
     L.bz2b200_reset_kernel_stats.restype = None
+    L.bz2b200_create_multi.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.bz2b200_destroy_multi.argtypes = [vp]
+    L.bz2b200_destroy_multi.restype = None
+    L.bz2b200_last_error_multi.argtypes = [vp]
+    L.bz2b200_last_error_multi.restype = C.c_char_p
+    L.bz2b200_multi_devices.argtypes = [vp]
+    L.bz2b200_multi_context.argtypes = [vp, C.c_int]
+    L.bz2b200_multi_context.restype = vp
+    L.bz2b200_compress_stream_multi.argtypes = [vp, u8p, C.c_size_t, C.c_int, u8p, C.c_size_t, szp]
+    L.bz2b200_multi_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 8)]
     _lib = L
     return L
 
@@ -364,6 +376,55 @@ class Engine:
         self._L.bz2b200_get_timing(self._h, C.byref(ms))
         names = ["rle1_crc_split", "bwt", "mtf_rle2", "huffman", "bitpack", "total"]
         return {k: float(ms[i]) for i, k in enumerate(names)}
+
+
+class MultiEngine:
+    """compress (compress.rs:40-136) on several GPUs of this process: ``bz2b200_mctx``.  `devices` = list of CUDA
+    device ids (an id may repeat: several ranks then share one GPU, which is how the single-GPU tests drive it)."""
+
+    def __init__(self, devices):
+        self._L = load_library()
+        ids = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._L.bz2b200_create_multi(len(devices), ids, C.byref(h))
+        if rc != OK:
+            raise Bz2B200Error(rc, "bz2b200_create_multi: no usable CUDA device (there is no CPU fallback)")
+        self._h = h
+        self.n = len(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bz2b200_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress_into(self, in_ptr, n, level, out_ptr, out_cap):
+        """Raw host pointers (page-locked for full overlap) -> compressed length."""
+        ln = C.c_size_t()
+        rc = self._L.bz2b200_compress_stream_multi(self._h, in_ptr, n, level, out_ptr, out_cap, C.byref(ln))
+        if rc != OK:
+            raise Bz2B200Error(rc, self._L.bz2b200_last_error_multi(self._h).decode())
+        return ln.value
+
+    def compress(self, data, level=9):
+        a = _np_u8(data)
+        cap = int(self._L.bz2b200_compress_bound(a.size))
+        out = np.empty(cap, dtype=np.uint8)
+        n = self.compress_into(a.ctypes.data, a.size, level, out.ctypes.data, cap)
+        return out[:n].tobytes()
+
+    def stats(self):
+        st = (C.c_uint64 * 8)()
+        self._L.bz2b200_multi_stats(self._h, C.byref(st))
+        return dict(h2d_bytes=int(st[0]), d2h_bytes=int(st[1]))
+
+    def launches(self):
+        return sum(int(self._L.bz2b200_launch_count(self._L.bz2b200_multi_context(self._h, r))) for r in range(self.n))
 
 
 _default = None

@@ -1,0 +1,353 @@
+// multi.cu -- ONE bzip2 stream compressed on N GPUs of one process: the fan-out / ordered fan-in of the reference's
+// `compress` (src/compression/compress.rs:40-136: par_bridge over blocks :125-132, writer thread :74-122) as a
+// library entry point.  No torch, no NCCL, no collective: blocks never exchange data.
+//
+//   The input is cut into windows of at most 256 MiB (a multiple of N of them, dealt round robin: window k belongs to
+//   rank k mod N; one window per rank when the input is small).  Rank r (one host thread + one context per GPU),
+//   for each of its windows:
+//     1. uploads the window (+ look-ahead for its last block) in chunks; the RLE1 scan follows the chunks
+//     2. receives the first block start of the window from the window before it (a host atomic: the block chain
+//        s_{k+1} = e(s_k) of rle1.rs:245-264 is sequential, but a link only needs the scans around it),
+//        chains its own blocks and hands the next start to the next window BEFORE the heavy work
+//     3. compresses its blocks into one bit string (no stream header / footer)
+//     4. publishes its bit count; once the counts of the windows before it are known it shifts the string to its
+//        final bit phase on the device and copies it over its own PCIe link straight into the caller's buffer
+//   the calling thread then ORs the seam bytes, folds the combined CRC in block order (crc.rs:25-27) and writes
+//   "BZh<level>" and the footer (bitwriter.rs:67-72, :103-114).
+// The output is the byte string a single bz2b200_compress_stream call produces, for any N.
+#include "common.cuh"
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <thread>
+
+int bz_shard_scan_upload(bz2b200_ctx *ctx, const u8 *h_src, u8 *d_win, size_t win_lo, size_t win_len, size_t n_total,
+                         int level, size_t chunk);
+
+namespace {
+
+struct MWin {                                // one input window
+    size_t lo = 0, hi = 0;
+    std::vector<u32> crcs;
+    u64 bits = 0;
+    u8 first_byte = 0;                       // of the shifted string when it shares a byte with the window before
+    size_t byte_lo = 0;
+    bool seam = false;
+    std::atomic<long long> chain_in{-1};     // first block start of this window (absolute input offset), written by window - 1
+    std::atomic<long long> bits_pub{-1};     // bit count, published when the window's blocks are compressed
+};
+struct MRank {
+    bz2b200_ctx *ctx = nullptr;
+    std::thread th;
+    DevBuf d_win, d_out, d_shift;
+    int rc = 0;
+    std::string err;
+    size_t h2d = 0, d2h = 0;
+    u32 nblk = 0;
+    double t_scan = 0, t_chain = 0, t_comp = 0, t_wait = 0, t_d2h = 0;
+};
+
+}  // namespace
+
+struct bz2b200_mctx {
+    int n = 0;
+    std::vector<std::unique_ptr<MRank>> rk;
+    std::vector<std::unique_ptr<MWin>> win;  // windows of the current call
+    std::mutex call_mu;                      // one compress call at a time
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    u64 seq = 0;
+    int done = 0;
+    bool quit = false;
+    // the job
+    const u8 *in = nullptr; size_t nbytes = 0; int level = 9; u8 *out = nullptr; size_t out_cap = 0;
+    std::atomic<int> abort{0};
+    std::string err;
+    u64 stat[8] = {0};
+};
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+inline double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
+
+
+// waits for a value >= 0 (or the abort flag); the hand-offs arrive within microseconds to a few milliseconds
+inline long long wait_value(bz2b200_mctx *m, std::atomic<long long> &a) {
+    for (int spin = 0;; spin++) {
+        if (m->abort.load(std::memory_order_relaxed)) return -1;
+        long long v = a.load(std::memory_order_acquire);
+        if (v >= 0) return v;
+        if (spin > 2000) std::this_thread::yield();
+    }
+}
+
+int rank_fail(bz2b200_mctx *m, MRank &R, int rc, const char *what) {
+    R.rc = rc;
+    R.err = std::string(what) + ": " + bz2b200_last_error(R.ctx);
+    m->abort.store(1);
+    return rc;
+}
+
+#define MCHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { R.rc = BZ2B200_E_CUDA; R.err = std::string(#call) + ": " + cudaGetErrorString(e_); m->abort.store(1); return R.rc; } } while (0)
+
+// one window on rank r
+int run_window(bz2b200_mctx *m, int r, size_t k) {
+    MRank &R = *m->rk[r];
+    MWin &W = *m->win[k];
+    bz2b200_ctx *ctx = R.ctx;
+    const int level = m->level;
+    const size_t n = m->nbytes, nwin = m->win.size();
+    const size_t lo = W.lo, hi = W.hi;
+    static const size_t CHUNK = [] { const char *e = getenv("BZ2B200_E2E_CHUNK_MB"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : v) << 20; }();
+    auto t0 = clk::now();
+    // ---- 1. upload + scan ----
+    size_t look = 4u << 20;                                     // look-ahead for the last block of the window, grown on demand
+    size_t win_len = std::min(n - lo, (hi - lo) + look);
+    size_t cap_out = bz2b200_compress_bound(hi - lo + (64u << 20));
+    MCHECK(R.d_win.ensure(std::min(n - lo, (hi - lo) + (64u << 20)) + 64));
+    MCHECK(R.d_out.ensure(cap_out + 64));
+    MCHECK(R.d_shift.ensure(cap_out + 128));
+    {
+        int rc = bz_shard_scan_upload(ctx, m->in + lo, R.d_win.as<u8>(), lo, win_len, n, level, CHUNK);
+        if (rc) return rank_fail(m, R, rc, "scan");
+        R.h2d += win_len;
+    }
+    R.t_scan += ms_since(t0);
+    // ---- 2. the chain ----
+    auto t1 = clk::now();
+    long long start = k == 0 ? 0 : wait_value(m, W.chain_in);
+    if (start < 0) return BZ2B200_E_CUDA;                      // another rank failed
+    R.t_wait += ms_since(t1);
+    auto t2 = clk::now();
+    size_t nxt = (size_t)start;
+    u32 nb = 0;
+    for (;;) {
+        int rc = bz2b200_shard_plan_dev(ctx, R.d_win.as<u8>(), lo, win_len, n, level, (size_t)start, hi, &nxt, &nb);
+        if (rc == BZ2B200_OK) break;
+        if (rc != BZ2B200_E_CAP || lo + win_len >= n) return rank_fail(m, R, rc, "plan");
+        // a block of this window spans more input than the look-ahead (long runs): lengthen the window and plan again
+        size_t new_len = std::min(n - lo, win_len + 8 * look);
+        look *= 8;
+        if (R.d_win.cap < new_len + 64) {                       // keep what is already resident
+            DevBuf bigger;
+            MCHECK(bigger.ensure(std::min(n - lo, 2 * new_len) + 64));
+            MCHECK(cudaMemcpyAsync(bigger.p, R.d_win.p, win_len, cudaMemcpyDeviceToDevice, ctx->stream));
+            MCHECK(cudaStreamSynchronize(ctx->stream));
+            R.d_win.release();
+            R.d_win = bigger;
+        }
+        MCHECK(cudaMemcpyAsync(R.d_win.as<u8>() + win_len, m->in + lo + win_len, new_len - win_len, cudaMemcpyHostToDevice, ctx->stream));
+        MCHECK(cudaStreamSynchronize(ctx->stream));
+        R.h2d += new_len - win_len;
+        win_len = new_len;
+    }
+    if (k + 1 < nwin) m->win[k + 1]->chain_in.store((long long)nxt, std::memory_order_release);
+    R.t_chain += ms_since(t2);
+    // ---- 3. compress ----
+    auto t3 = clk::now();
+    W.bits = 0;
+    if (nb) {
+        W.crcs.resize(nb);
+        int rc = bz2b200_shard_compress_dev(ctx, R.d_out.as<u8>(), cap_out & ~(size_t)3, &W.bits, W.crcs.data());
+        if (rc) return rank_fail(m, R, rc, "compress");
+        R.nblk += nb;
+    }
+    W.bits_pub.store((long long)W.bits, std::memory_order_release);
+    R.t_comp += ms_since(t3);
+    // ---- 4. final position, shift, download ----
+    auto t4 = clk::now();
+    u64 off = 32;
+    for (size_t q = 0; q < k; q++) {
+        long long b = wait_value(m, m->win[q]->bits_pub);
+        if (b < 0) return BZ2B200_E_CUDA;
+        off += (u64)b;
+    }
+    if (W.bits) {
+        int phase = (int)(off & 7);
+        size_t nby = (size_t)((W.bits + phase + 7) / 8);
+        W.byte_lo = (size_t)(off >> 3);
+        if (W.byte_lo + nby + 16 > m->out_cap) { R.rc = BZ2B200_E_CAP; R.err = "output buffer too small"; m->abort.store(1); return R.rc; }
+        int rc = bz2b200_shift_bits_dev(ctx, R.d_out.as<u8>(), W.bits, phase, R.d_shift.as<u8>());
+        if (rc) return rank_fail(m, R, rc, "shift");
+        W.seam = phase != 0;                                    // the first byte is shared with whatever precedes (window 0: phase 0)
+        size_t skip = W.seam ? 1 : 0;
+        if (W.seam) MCHECK(cudaMemcpyAsync(&W.first_byte, R.d_shift.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        if (nby > skip) MCHECK(cudaMemcpyAsync(m->out + W.byte_lo + skip, R.d_shift.as<u8>() + skip, nby - skip, cudaMemcpyDeviceToHost, ctx->stream));
+        MCHECK(cudaStreamSynchronize(ctx->stream));
+        R.d2h += nby;
+    }
+    R.t_d2h += ms_since(t4);
+    return BZ2B200_OK;
+}
+
+int run_rank(bz2b200_mctx *m, int r) {
+    MRank &R = *m->rk[r];
+    R.rc = 0; R.err.clear(); R.h2d = R.d2h = 0; R.nblk = 0;
+    R.t_scan = R.t_chain = R.t_comp = R.t_wait = R.t_d2h = 0;
+    MCHECK(cudaSetDevice(R.ctx->device));
+    for (size_t k = (size_t)r; k < m->win.size(); k += (size_t)m->n) {
+        int rc = run_window(m, r, k);
+        if (rc) return rc;
+    }
+    return BZ2B200_OK;
+}
+
+void worker(bz2b200_mctx *m, int r) {
+    u64 seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(m->mu);
+            m->cv_job.wait(lk, [&] { return m->quit || m->seq != seen; });
+            if (m->quit) return;
+            seen = m->seq;
+        }
+        int rc;
+        try { rc = run_rank(m, r); } catch (...) { rc = BZ2B200_E_NOMEM; m->rk[r]->rc = rc; m->rk[r]->err = "out of memory"; m->abort.store(1); }
+        (void)rc;                                               // a failed rank has raised the abort flag: nobody waits for it
+        {
+            std::lock_guard<std::mutex> lk(m->mu);
+            m->done++;
+        }
+        m->cv_done.notify_all();
+    }
+}
+
+inline u32 crc_step(u32 s, u32 b) { return ((s << 1) | (s >> 31)) ^ b; }   // crc.rs:25-27
+
+}  // namespace
+
+extern "C" {
+
+int bz2b200_create_multi(int n_devices, const int *device_ids, bz2b200_mctx **out) {
+    BZ_API_TRY
+    if (!out || n_devices < 1 || n_devices > 64) return BZ2B200_E_ARG;
+    *out = nullptr;
+    std::unique_ptr<bz2b200_mctx> m(new bz2b200_mctx());
+    m->n = n_devices;
+    for (int r = 0; r < n_devices; r++) {
+        m->rk.emplace_back(new MRank());
+        int rc = bz2b200_create(device_ids ? device_ids[r] : r, &m->rk[r]->ctx);
+        if (rc) {
+            for (auto &R : m->rk) if (R->ctx) bz2b200_destroy(R->ctx);
+            return rc;
+        }
+    }
+    for (int r = 0; r < n_devices; r++) m->rk[r]->th = std::thread(worker, m.get(), r);
+    *out = m.release();
+    return BZ2B200_OK;
+    BZ_API_CATCH
+}
+
+void bz2b200_destroy_multi(bz2b200_mctx *m) {
+    if (!m) return;
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->quit = true;
+    }
+    m->cv_job.notify_all();
+    for (auto &R : m->rk) if (R->th.joinable()) R->th.join();
+    for (auto &R : m->rk) {
+        if (R->ctx) {
+            cudaSetDevice(R->ctx->device);
+            R->d_win.release(); R->d_out.release(); R->d_shift.release();
+            bz2b200_destroy(R->ctx);
+        }
+    }
+    delete m;
+}
+
+const char *bz2b200_last_error_multi(const bz2b200_mctx *m) { return m ? m->err.c_str() : "null context"; }
+int bz2b200_multi_devices(const bz2b200_mctx *m) { return m ? m->n : 0; }
+bz2b200_ctx *bz2b200_multi_context(bz2b200_mctx *m, int rank) { return (m && rank >= 0 && rank < m->n) ? m->rk[rank]->ctx : nullptr; }
+
+int bz2b200_compress_stream_multi(bz2b200_mctx *m, const uint8_t *in, size_t n, int level, uint8_t *out,
+                                  size_t out_cap, size_t *out_len) {
+    BZ_API_TRY
+    if (!m || (!in && n) || !out || !out_len || level < 1 || level > 9) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> call(m->call_mu);
+    // small inputs (or one device): the single-GPU path, same bytes
+    if (m->n == 1 || n < (size_t)m->n * (8u << 20)) {
+        int rc = bz2b200_compress_stream(m->rk[0]->ctx, in, n, level, out, out_cap, out_len);
+        if (rc) m->err = bz2b200_last_error(m->rk[0]->ctx);
+        m->stat[0] = n; m->stat[1] = rc ? 0 : *out_len;
+        return rc;
+    }
+    if (out_cap < 64) return BZ2B200_E_CAP;
+    auto t0 = clk::now();
+    m->in = in; m->nbytes = n; m->level = level; m->out = out; m->out_cap = out_cap;
+    m->abort.store(0);
+    {   // windows: a multiple of n_devices, at most 256 MiB each, whole 4 KiB pages
+        const size_t WMAX = 256u << 20;
+        size_t per_rank = (n + (size_t)m->n - 1) / (size_t)m->n;
+        size_t nwin = (size_t)m->n * ((per_rank + WMAX - 1) / WMAX);
+        size_t wsz = (((n + nwin - 1) / nwin) + 4095) & ~(size_t)4095;
+        m->win.clear();
+        for (size_t lo = 0; lo < n; lo += wsz) {
+            m->win.emplace_back(new MWin());
+            m->win.back()->lo = lo;
+            m->win.back()->hi = std::min(n, lo + wsz);
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->done = 0;
+        m->seq++;
+    }
+    m->cv_job.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(m->mu);
+        m->cv_done.wait(lk, [&] { return m->done == m->n; });
+    }
+    for (auto &R : m->rk) {
+        if (R->rc) { m->err = "rank failed: " + R->err; return R->rc; }
+    }
+    // ---- ordered fan-in on the host: seam bytes, combined CRC, header, footer ----
+    u64 pos = 32;
+    u32 combined = 0;
+    for (auto &W : m->win) {
+        if (W->bits) {
+            if (W->seam) out[W->byte_lo] |= W->first_byte;
+            pos += W->bits;
+        }
+        for (u32 c : W->crcs) combined = crc_step(combined, c);            // bitwriter.rs:89-91
+    }
+    out[0] = 'B'; out[1] = 'Z'; out[2] = 'h'; out[3] = (u8)('0' + level);  // bitwriter.rs:67-72
+    size_t len = (size_t)((pos + 80 + 7) / 8);
+    if (len > out_cap) return BZ2B200_E_CAP;
+    const u8 foot[10] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90, (u8)(combined >> 24), (u8)(combined >> 16), (u8)(combined >> 8), (u8)combined};
+    const int sh = (int)(pos & 7);
+    u8 *d = out + (pos >> 3);
+    if (sh == 0) d[0] = 0;                                      // otherwise the byte holds the last bits of the last block
+    for (size_t j = 1; j <= 10 && (size_t)(pos >> 3) + j < len; j++) d[j] = 0;
+    for (int j = 0; j < 10; j++) {                              // bitwriter.rs:103-114
+        d[j] |= (u8)(foot[j] >> sh);
+        if (sh) d[j + 1] |= (u8)(foot[j] << (8 - sh));
+    }
+    *out_len = len;
+    u64 h2d = 0, d2h = 0;
+    for (auto &R : m->rk) { h2d += R->h2d; d2h += R->d2h; }
+    m->stat[0] = h2d; m->stat[1] = d2h;
+    if (getenv("BZ2B200_MULTI_TRACE")) {
+        fprintf(stderr, "[multi] total %.2f ms\n", ms_since(t0));
+        for (int r = 0; r < m->n; r++) {
+            MRank &R = *m->rk[r];
+            fprintf(stderr, "[multi rank %d] upload+scan %.2f wait %.2f chain %.2f compress %.2f offsets+shift+d2h %.2f ms, %u blocks\n", r,
+                    R.t_scan, R.t_wait, R.t_chain, R.t_comp, R.t_d2h, (unsigned)R.nblk);
+        }
+    }
+    return BZ2B200_OK;
+    BZ_API_CATCH
+}
+
+int bz2b200_multi_stats(const bz2b200_mctx *m, uint64_t st[8]) {
+    if (!m || !st) return BZ2B200_E_ARG;
+    memcpy(st, m->stat, sizeof(u64) * 8);
+    return BZ2B200_OK;
+}
+
+}  // extern "C"

@@ -112,6 +112,29 @@ int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, con
                           const uint32_t *const *part_crcs, const uint32_t *part_ncrc,
                           uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* ---- seam: compress (src/compression/compress.rs:40-136) on SEVERAL GPUs of one process -------------------- */
+/* The reference fans blocks out to rayon workers (compress.rs:125-132) and a writer thread puts them back in
+ * order (compress.rs:74-122).  A multi context owns n_devices single-GPU contexts and one host thread per GPU
+ * (device_ids == NULL: devices 0 .. n_devices-1; an id may repeat).  bz2b200_compress_stream_multi cuts the input
+ * into n_devices contiguous slices; every GPU uploads and scans its slice, the block chain (rle1.rs:245-264) is
+ * handed from GPU to GPU as one number through host memory, every GPU compresses the blocks that start in its
+ * slice and copies its bit string, pre-shifted to its final bit phase, over its own PCIe link straight into
+ * `out`; the calling thread ORs the seam bytes, folds the combined CRC (crc.rs:25-27) and writes header and
+ * footer (bitwriter.rs:67-72, :103-114).  No collective, no NCCL.  `out` holds exactly the bytes
+ * bz2b200_compress_stream produces for the same input, for every n_devices.  Pass page-locked `in` / `out`
+ * for full copy overlap.  One call at a time per multi context. */
+typedef struct bz2b200_mctx bz2b200_mctx;
+int  bz2b200_create_multi(int n_devices, const int *device_ids, bz2b200_mctx **out);
+void bz2b200_destroy_multi(bz2b200_mctx *m);
+const char *bz2b200_last_error_multi(const bz2b200_mctx *m);
+int  bz2b200_multi_devices(const bz2b200_mctx *m);
+/* the single-GPU context of one rank (timing / statistics hooks); owned by the multi context */
+bz2b200_ctx *bz2b200_multi_context(bz2b200_mctx *m, int rank);
+int  bz2b200_compress_stream_multi(bz2b200_mctx *m, const uint8_t *in, size_t n, int level,
+                                   uint8_t *out, size_t out_cap, size_t *out_len);
+/* last call: [0] = bytes copied host -> device (all GPUs), [1] = device -> host */
+int  bz2b200_multi_stats(const bz2b200_mctx *m, uint64_t st[8]);
+
 /* ---- stage seams (used by the parity tests, one per reference function) ------------------ */
 /* do_crc (src/tools/crc.rs:15) */
 int bz2b200_crc32(bz2b200_ctx *ctx, const uint8_t *data, size_t n, uint32_t *crc);
