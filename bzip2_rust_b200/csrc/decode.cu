@@ -182,19 +182,70 @@ extern "C" int bz2b200_bwt_decode(bz2b200_ctx *ctx, uint32_t key, const uint8_t 
     BZ_API_CATCH
 }
 
+// ---- legacy randomised blocks (bzip2 <= 0.9.0): the un-BWT'd bytes are XORed with 1 at pseudo-random distances ----
+// The 512 distances are a constant of the .bz2 format (BZ2_rNums of libbz2; the reference keeps the same numbers in
+// src/unused/randomizing_table.rs:1-32 without using them, its decoder ignores the flag).  Byte i of the block is
+// flipped when the countdown started from the current table entry stands at 1, i.e. at cum(t) + rNums[t] - 2.
+__constant__ u16 c_rnums[512] = {
+    619, 720, 127, 481, 931, 816, 813, 233, 566, 247, 985, 724, 205, 454, 863, 491, 741, 242, 949, 214, 733, 859, 335, 708,
+    621, 574, 73, 654, 730, 472, 419, 436, 278, 496, 867, 210, 399, 680, 480, 51, 878, 465, 811, 169, 869, 675, 611, 697,
+    867, 561, 862, 687, 507, 283, 482, 129, 807, 591, 733, 623, 150, 238, 59, 379, 684, 877, 625, 169, 643, 105, 170, 607,
+    520, 932, 727, 476, 693, 425, 174, 647, 73, 122, 335, 530, 442, 853, 695, 249, 445, 515, 909, 545, 703, 919, 874, 474,
+    882, 500, 594, 612, 641, 801, 220, 162, 819, 984, 589, 513, 495, 799, 161, 604, 958, 533, 221, 400, 386, 867, 600, 782,
+    382, 596, 414, 171, 516, 375, 682, 485, 911, 276, 98, 553, 163, 354, 666, 933, 424, 341, 533, 870, 227, 730, 475, 186,
+    263, 647, 537, 686, 600, 224, 469, 68, 770, 919, 190, 373, 294, 822, 808, 206, 184, 943, 795, 384, 383, 461, 404, 758,
+    839, 887, 715, 67, 618, 276, 204, 918, 873, 777, 604, 560, 951, 160, 578, 722, 79, 804, 96, 409, 713, 940, 652, 934,
+    970, 447, 318, 353, 859, 672, 112, 785, 645, 863, 803, 350, 139, 93, 354, 99, 820, 908, 609, 772, 154, 274, 580, 184,
+    79, 626, 630, 742, 653, 282, 762, 623, 680, 81, 927, 626, 789, 125, 411, 521, 938, 300, 821, 78, 343, 175, 128, 250,
+    170, 774, 972, 275, 999, 639, 495, 78, 352, 126, 857, 956, 358, 619, 580, 124, 737, 594, 701, 612, 669, 112, 134, 694,
+    363, 992, 809, 743, 168, 974, 944, 375, 748, 52, 600, 747, 642, 182, 862, 81, 344, 805, 988, 739, 511, 655, 814, 334,
+    249, 515, 897, 955, 664, 981, 649, 113, 974, 459, 893, 228, 433, 837, 553, 268, 926, 240, 102, 654, 459, 51, 686, 754,
+    806, 760, 493, 403, 415, 394, 687, 700, 946, 670, 656, 610, 738, 392, 760, 799, 887, 653, 978, 321, 576, 617, 626, 502,
+    894, 679, 243, 440, 680, 879, 194, 572, 640, 724, 926, 56, 204, 700, 707, 151, 457, 449, 797, 195, 791, 558, 945, 679,
+    297, 59, 87, 824, 713, 663, 412, 693, 342, 606, 134, 108, 571, 364, 631, 212, 174, 643, 304, 329, 343, 97, 430, 751,
+    497, 314, 983, 374, 822, 928, 140, 206, 73, 263, 980, 736, 876, 478, 430, 305, 170, 514, 364, 692, 829, 82, 855, 953,
+    676, 246, 369, 970, 294, 750, 807, 827, 150, 790, 288, 923, 804, 378, 215, 828, 592, 281, 565, 555, 710, 82, 896, 831,
+    547, 261, 524, 462, 293, 465, 502, 56, 661, 821, 976, 991, 658, 869, 905, 758, 745, 193, 768, 550, 608, 933, 378, 286,
+    215, 979, 792, 961, 61, 688, 793, 644, 986, 403, 106, 366, 905, 644, 372, 567, 466, 434, 645, 210, 389, 550, 919, 135,
+    780, 773, 635, 389, 707, 100, 626, 958, 165, 504, 920, 176, 193, 713, 857, 265, 203, 50, 668, 108, 645, 990, 626, 197,
+    510, 357, 358, 850, 858, 364, 936, 638};
+
+// one CTA per block, thread per table entry (cycled): flips of a randomised block
+__global__ void __launch_bounds__(512) k_derandomize(u8 *blk, const u32 *len, const u32 *randflag, u32 stride) {
+    u32 b = blockIdx.x;
+    if (!randflag[b]) return;
+    u32 n = len[b];
+    __shared__ u32 cum[513];
+    if (threadIdx.x == 0) { u32 a = 0; for (int t = 0; t < 512; t++) { cum[t] = a; a += c_rnums[t]; } cum[512] = a; }
+    __syncthreads();
+    u8 *x = blk + (size_t)b * stride;
+    const u32 period = cum[512];
+    for (u32 base = 0; base < n; base += period) {
+        u32 pos = base + cum[threadIdx.x] + c_rnums[threadIdx.x] - 2u;
+        if (pos < n) x[pos] ^= 1;
+    }
+}
+
+namespace {
+struct DecTail { u32 T, alpha, G, status, crc, key; u64 data_bit, end_bit; u32 nsym, ngroups, nblock, pad; };
+static_assert(sizeof(DecTail) == sizeof(DecTables) - offsetof(DecTables, T), "DecTail mirrors the tail of DecTables");
+constexpr u64 FOOT = 1ull << 63;
+constexpr u32 DEC_BATCH = 128;           // candidate blocks decoded per pass (one pass for 100 MB at level 9)
+}  // namespace
+
 extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
                                          size_t *out_len) {
     BZ_API_TRY
-    if (!ctx || !in || !out_len || (!out && out_cap) || n < 14) return BZ2B200_E_ARG;
+    if (!ctx || !in || !out_len || (!out && out_cap) || n < 14 || n > 0xFFFFFF00ull * 4ull) return BZ2B200_E_ARG;
     if (in[0] != 'B' || in[1] != 'Z' || in[2] != 'h' || in[3] < '1' || in[3] > '9') return BZ2B200_E_FORMAT;   // decompress.rs:46-62
-    int level = in[3] - '0';
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     cudaStream_t st = ctx->stream;
+    *out_len = 0;
     BZ_CHECK(ctx->d_in.ensure(n + 64));
     BZ_CHECK(cudaMemcpyAsync(ctx->d_in.p, in, n, cudaMemcpyHostToDevice, st));
-    // ---- 1. block starts ----
-    u32 cap = (u32)(n / 32 + 64);
+    // ---- 1. every bit offset that looks like a block or footer magic ----
+    u32 cap = (u32)std::min<size_t>(n / 32 + 64, 0x7fffff00u);
     BZ_CHECK(ctx->d_dec1.ensure((size_t)cap * 8 + 64));
     u64 *d_cand = ctx->d_dec1.as<u64>();
     u32 *d_ncand = (u32 *)(d_cand + cap);
@@ -206,117 +257,156 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     if (ncand == 0 || ncand > cap) return BZ2B200_E_FORMAT;
     std::vector<u64> cand(ncand);
     BZ_CHECK(cudaMemcpy(cand.data(), d_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost));
-    std::sort(cand.begin(), cand.end(), [](u64 a, u64 b) { return (a & ~(1ull << 63)) < (b & ~(1ull << 63)); });
-    if ((cand[0] & ~(1ull << 63)) != 32) return BZ2B200_E_FORMAT;
-    // blocks = candidates up to the first footer magic that is followed by the end of the stream
-    std::vector<u64> starts;
-    u64 footer_bit = 0; bool have_footer = false;
-    for (u64 c : cand) {
-        u64 bit = c & ~(1ull << 63);
-        if (c >> 63) { if ((bit + 80 + 7) / 8 == (u64)n) { footer_bit = bit; have_footer = true; break; } continue; }
-        starts.push_back(bit);
+    std::sort(cand.begin(), cand.end(), [](u64 a, u64 b) { return (a & ~FOOT) < (b & ~FOOT); });
+    // A magic can also occur by chance inside entropy-coded data, and a file may hold several streams one after the
+    // other (decompress.rs handles neither; libbz2 walks the blocks serially and accepts both).  So the candidates are
+    // only where blocks MAY start: the chain is walked from every decoded block's end, candidates off the chain are
+    // dropped, and a footer that is not the end of the input must be followed by the next stream's "BZh<level>".
+    int level = in[3] - '0';
+    for (u64 c : cand) {                                        // geometry: the largest block size any stream header announces
+        if (!(c & FOOT)) continue;
+        size_t hb = (size_t)(((c & ~FOOT) + 80 + 7) / 8);
+        if (hb + 4 <= n && in[hb] == 'B' && in[hb + 1] == 'Z' && in[hb + 2] == 'h' && in[hb + 3] >= '1' && in[hb + 3] <= '9')
+            level = std::max(level, in[hb + 3] - '0');
     }
-    if (!have_footer) return BZ2B200_E_FORMAT;
-    u32 nb = (u32)starts.size();
-    u32 stored_combined = 0;
-    {
-        size_t byte = (size_t)((footer_bit + 48) >> 3); int sh = (int)((footer_bit + 48) & 7);
-        u64 w = 0;
-        for (int k = 0; k < 5; k++) w = (w << 8) | (byte + k < n ? in[byte + k] : 0);
-        stored_combined = (u32)((w >> (8 - sh)) & 0xffffffffull);
-    }
-    if (nb == 0) { *out_len = 0; return stored_combined == 0 ? BZ2B200_OK : BZ2B200_E_CRC; }
-    // ---- 2. entropy decode (decode4.cuh) ----
-    u32 max_block = (u32)level * 100000u;
-    u32 stride = ((max_block + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE;
-    u32 sel_stride = max_block / 50 + 8;
-    u32 max_sym = max_block + 2;                                 // every symbol but EOB yields at least one byte
-    u32 sym_stride = ((max_sym + 64 + DCH - 1) / DCH) * DCH;
-    u32 ch_stride = sym_stride / DCH + 2;
-    BZ_CHECK(ctx->d_T.ensure((size_t)nb * stride + 64));
-    BZ_CHECK(ctx->d_bwt.ensure((size_t)nb * stride + 64));
-    BZ_CHECK(ctx->d_sel.ensure((size_t)nb * sel_stride));
-    BZ_CHECK(ctx->d_gbits.ensure((size_t)nb * sel_stride * 4));
-    BZ_CHECK(ctx->d_sym.ensure((size_t)nb * sym_stride * 2));
-    BZ_CHECK(ctx->d_mtfstate.ensure((size_t)nb * ch_stride * 256));
-    BZ_CHECK(ctx->d_chunkrec.ensure((size_t)nb * ch_stride * 8));
-    BZ_CHECK(ctx->d_hdr.ensure((size_t)nb * sizeof(DecTables)));
-    BZ_CHECK(ctx->d_dec3.ensure((size_t)nb * (8 + 4 + 4 + 8 + 8 + 8) + 256));
+    const u32 max_block = (u32)level * 100000u;
+    const u32 stride = ((max_block + 64 + BZ_TILE - 1) / BZ_TILE) * BZ_TILE;
+    const u32 sel_stride = max_block / 50 + 8;
+    const u32 max_sym = max_block + 2;                           // every symbol but EOB yields at least one byte
+    const u32 sym_stride = ((max_sym + 64 + DCH - 1) / DCH) * DCH;
+    const u32 ch_stride = sym_stride / DCH + 2;
+    const u32 NB = DEC_BATCH;
+    BZ_CHECK(ctx->d_T.ensure((size_t)NB * stride + 64));
+    BZ_CHECK(ctx->d_bwt.ensure((size_t)NB * stride + 64));
+    BZ_CHECK(ctx->d_sel.ensure((size_t)NB * sel_stride));
+    BZ_CHECK(ctx->d_gbits.ensure((size_t)NB * sel_stride * 4));
+    BZ_CHECK(ctx->d_sym.ensure((size_t)NB * sym_stride * 2));
+    BZ_CHECK(ctx->d_mtfstate.ensure((size_t)NB * ch_stride * 256));
+    BZ_CHECK(ctx->d_chunkrec.ensure((size_t)NB * ch_stride * 8));
+    BZ_CHECK(ctx->d_hdr.ensure((size_t)NB * sizeof(DecTables)));
+    BZ_CHECK(ctx->d_dec3.ensure((size_t)NB * (8 + 4 + 4 + 4 + 8 + 8 + 8) + 256));
+    BZ_CHECK(ctx->d_crc.ensure((size_t)NB * 4));
     DecTables *d_tabs = ctx->d_hdr.as<DecTables>();
     u32 *d_gbit = ctx->d_gbits.as<u32>();
     u16 *d_sym = ctx->d_sym.as<u16>();
     u8 *d_lists = ctx->d_mtfstate.as<u8>();
     u32 *d_ccount = ctx->d_chunkrec.as<u32>();
-    u32 *d_coff = d_ccount + (size_t)nb * ch_stride;
+    u32 *d_coff = d_ccount + (size_t)NB * ch_stride;
     u64 *d_starts = ctx->d_dec3.as<u64>();
-    u32 *d_len = (u32 *)(d_starts + nb);
-    const u32 nbp = (nb + 1) & ~1u;                              // keep the u64 arrays 8-byte aligned
-    u32 *d_keys = d_len + nbp;
-    u64 *d_olen = (u64 *)(d_keys + nbp);
-    u64 *d_ooff = d_olen + nb;
-    u32 *d_se = (u32 *)(d_ooff + nb);
+    u64 *d_olen = d_starts + NB;
+    u64 *d_ooff = d_olen + NB;
+    u32 *d_len = (u32 *)(d_ooff + NB);
+    u32 *d_keys = d_len + NB;
+    u32 *d_rand = d_keys + NB;
+    u32 *d_se = d_rand + NB;
     const u8 *d_bits = ctx->d_in.as<u8>();
-    BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_HEADER, 0); k_dec_header<<<nb, 32, 0, st>>>(d_bits, n, d_starts, ctx->d_sel.as<u8>(), sel_stride, d_tabs); LAUNCH_OK();
     if (!ctx->dec_attr_done) { BZ_CHECK(cudaFuncSetAttribute(k_dec_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BoundsSmem))); ctx->dec_attr_done = true; }
-    ctx->prof_begin(K_DEC_BOUNDS, n); k_dec_bounds<<<nb, 32, sizeof(BoundsSmem), st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, max_sym); LAUNCH_OK();
-    dim3 gs((sel_stride + 127) / 128, nb);
-    ctx->prof_begin(K_DEC_SYMS, n); k_dec_syms<<<gs, 128, 0, st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, d_sym, sym_stride); LAUNCH_OK();
-    dim3 gch((ch_stride + 7) / 8, nb);
-    ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<0><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
-    ctx->prof_begin(K_DEC_CHUNK_SCAN, 0); k_dec_chunk_scan<<<nb, 256, 0, st>>>(d_tabs, d_lists, d_ccount, d_coff, ch_stride, max_block); LAUNCH_OK();
-    ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<1><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
-    // per-block results: the tail of DecTables (T .. pad)
-    struct DecTail { u32 T, alpha, G, status, crc, key; u64 data_bit, end_bit; u32 nsym, ngroups, nblock, pad; };
-    static_assert(sizeof(DecTail) == sizeof(DecTables) - offsetof(DecTables, T), "DecTail mirrors the tail of DecTables");
-    std::vector<DecTail> db(nb);
-    BZ_CHECK(cudaMemcpy2DAsync(db.data(), sizeof(DecTail), (const u8 *)d_tabs + offsetof(DecTables, T), sizeof(DecTables),
-                               sizeof(DecTail), nb, cudaMemcpyDeviceToHost, st));
-    BZ_CHECK(cudaStreamSynchronize(st));
-    std::vector<u32> hlen(nb), hkey(nb);
-    u32 combined = 0, max_n = 0; u64 total_n = 0;
-    for (u32 k = 0; k < nb; k++) {
-        if (db[k].status != 0) { ctx->err = "decode: block " + std::to_string(k) + " status " + std::to_string(db[k].status); return BZ2B200_E_FORMAT; }
-        u64 next = k + 1 < nb ? starts[k + 1] : footer_bit;
-        if (db[k].end_bit != next) { ctx->err = "decode: block " + std::to_string(k) + " does not end at the next block magic"; return BZ2B200_E_FORMAT; }
-        hlen[k] = db[k].nblock; hkey[k] = db[k].key;
-        max_n = std::max(max_n, hlen[k]); total_n += hlen[k];
-        combined = ((combined << 1) | (combined >> 31)) ^ db[k].crc;
+
+    auto read32 = [&](u64 bit) {                                // 32 bits at an arbitrary bit offset of the input
+        size_t byte = (size_t)(bit >> 3); int sh = (int)(bit & 7);
+        u64 w = 0;
+        for (int k = 0; k < 5; k++) w = (w << 8) | (byte + k < n ? in[byte + k] : 0);
+        return (u32)((w >> (8 - sh)) & 0xffffffffull);
+    };
+    size_t ci = 0;                                              // next candidate to look at
+    u64 expect = 32;                                            // bit offset where the next block / footer must start
+    u32 combined = 0;                                           // running combined CRC of the current stream
+    size_t total_out = 0;
+    std::vector<u64> starts;
+    std::vector<DecTail> db;
+    std::vector<u32> hlen(NB), hkey(NB), hrand(NB), se(2 * (size_t)NB), crcs(NB);
+    std::vector<u64> olen(NB), ooff(NB);
+    for (;;) {
+        while (ci < ncand && (cand[ci] & ~FOOT) < expect) ci++;
+        if (ci == ncand || (cand[ci] & ~FOOT) != expect) { ctx->err = "decode: no block or footer magic at bit " + std::to_string(expect); return BZ2B200_E_FORMAT; }
+        if (cand[ci] & FOOT) {                                  // end of a stream: combined CRC, then end of input or another stream
+            if (read32(expect + 48) != combined) return BZ2B200_E_CRC;                        // enforced, unlike decompress.rs:394-402
+            size_t hb = (size_t)((expect + 80 + 7) / 8);
+            if (hb == n) break;
+            if (hb + 4 > n || in[hb] != 'B' || in[hb + 1] != 'Z' || in[hb + 2] != 'h' || in[hb + 3] < '1' || in[hb + 3] > '9') {
+                ctx->err = "decode: trailing bytes after the stream footer"; return BZ2B200_E_FORMAT;
+            }
+            combined = 0;
+            expect = (u64)hb * 8 + 32;
+            continue;
+        }
+        // ---- 2. entropy decode of the next candidate blocks (decode4.cuh) ----
+        starts.clear();
+        for (size_t k = ci; k < ncand && starts.size() < NB; k++) if (!(cand[k] & FOOT)) starts.push_back(cand[k]);
+        const u32 nb = (u32)starts.size();
+        BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+        ctx->prof_begin(K_DEC_HEADER, 0); k_dec_header<<<nb, 32, 0, st>>>(d_bits, n, d_starts, ctx->d_sel.as<u8>(), sel_stride, d_tabs); LAUNCH_OK();
+        ctx->prof_begin(K_DEC_BOUNDS, n); k_dec_bounds<<<nb, 32, sizeof(BoundsSmem), st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, max_sym); LAUNCH_OK();
+        dim3 gs((sel_stride + 127) / 128, nb);
+        ctx->prof_begin(K_DEC_SYMS, n); k_dec_syms<<<gs, 128, 0, st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, d_sym, sym_stride); LAUNCH_OK();
+        dim3 gch((ch_stride + 7) / 8, nb);
+        ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<0><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
+        ctx->prof_begin(K_DEC_CHUNK_SCAN, 0); k_dec_chunk_scan<<<nb, 256, 0, st>>>(d_tabs, d_lists, d_ccount, d_coff, ch_stride, max_block); LAUNCH_OK();
+        ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<1><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
+        db.resize(nb);
+        BZ_CHECK(cudaMemcpy2DAsync(db.data(), sizeof(DecTail), (const u8 *)d_tabs + offsetof(DecTables, T), sizeof(DecTables),
+                                   sizeof(DecTail), nb, cudaMemcpyDeviceToHost, st));
+        BZ_CHECK(cudaStreamSynchronize(st));
+        // ---- the chain inside this batch: candidate k is a block iff the block before it ends exactly there ----
+        u32 max_n = 0, used = 0; u64 total_n = 0;
+        for (u32 k = 0; k < nb; k++) {
+            hlen[k] = 0; hkey[k] = 0; hrand[k] = 0;
+            if (starts[k] != expect) continue;                  // inside another block's data: not a block
+            if (db[k].status != 0) { ctx->err = "decode: block at bit " + std::to_string(starts[k]) + " status " + std::to_string(db[k].status); return BZ2B200_E_FORMAT; }
+            if (db[k].key >= db[k].nblock) { ctx->err = "decode: origin pointer outside the block"; return BZ2B200_E_FORMAT; }
+            hlen[k] = db[k].nblock; hkey[k] = db[k].key; hrand[k] = db[k].pad;
+            max_n = std::max(max_n, hlen[k]); total_n += hlen[k];
+            combined = ((combined << 1) | (combined >> 31)) ^ db[k].crc;                       // crc.rs:25-27
+            expect = db[k].end_bit;
+            used = k + 1;
+        }
+        if (used == 0) { ctx->err = "decode: lost the block chain"; return BZ2B200_E_FORMAT; }
+        // candidates up to the last block of the chain are consumed (the next loop skips what lies below `expect`)
+        while (ci < ncand && (cand[ci] & ~FOOT) <= starts[used - 1]) ci++;
+        BZ_CHECK(cudaMemcpyAsync(d_len, hlen.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        BZ_CHECK(cudaMemcpyAsync(d_keys, hkey.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        BZ_CHECK(cudaMemcpyAsync(d_rand, hrand.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        // ---- 3. inverse BWT (+ de-randomisation of legacy blocks) ----
+        Batch B;
+        B.nblk = (int)used; B.stride = stride; B.tiles = stride / BZ_TILE; B.max_n = max_n; B.nbits = 20; B.T = ctx->d_T.as<u8>();
+        B.len = d_len; B.total_n = total_n;
+        int rc = ibwt_batch(ctx, B, d_keys, ctx->d_bwt.as<u8>());
+        if (rc) return rc;
+        bool any_rand = false;
+        for (u32 k = 0; k < used; k++) any_rand |= hrand[k] != 0;
+        if (any_rand) { ctx->prof_begin(K_DEC_MISC, total_n); k_derandomize<<<used, 512, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, d_rand, stride); LAUNCH_OK(); }
+        // ---- 4. inverse RLE1 + CRC; the batch's bytes go to out + total_out ----
+        ctx->prof_begin(K_DEC_RLE1_COUNT, total_n); k_rle1_inv<0><<<used, 256, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_olen, nullptr, nullptr); LAUNCH_OK();
+        BZ_CHECK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)used * 8, cudaMemcpyDeviceToHost, st));
+        BZ_CHECK(cudaStreamSynchronize(st));
+        u64 btotal = 0;
+        for (u32 k = 0; k < used; k++) { ooff[k] = btotal; btotal += olen[k]; }
+        *out_len = total_out + (size_t)btotal;
+        if (total_out + btotal > out_cap) return BZ2B200_E_CAP;
+        BZ_CHECK(ctx->d_stream.ensure((size_t)btotal + 64));
+        BZ_CHECK(cudaMemcpyAsync(d_ooff, ooff.data(), (size_t)used * 8, cudaMemcpyHostToDevice, st));
+        ctx->prof_begin(K_DEC_RLE1_WRITE, btotal); k_rle1_inv<1><<<used, 256, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, nullptr, d_ooff, ctx->d_stream.as<u8>()); LAUNCH_OK();
+        // block CRCs in sub-ranges of at most 2 GiB of output (a block decodes to at most ~46 MB; spans are 32-bit)
+        for (u32 k0 = 0; k0 < used;) {
+            u32 k1 = k0; u64 sub = 0, max_span = 0;
+            while (k1 < used && (k1 == k0 || sub + olen[k1] <= (1ull << 31))) {
+                se[2 * k1] = (u32)sub; se[2 * k1 + 1] = (u32)(sub + olen[k1]);
+                sub += olen[k1]; max_span = std::max(max_span, olen[k1]); k1++;
+            }
+            BZ_CHECK(cudaMemcpyAsync(d_se + 2 * k0, se.data() + 2 * k0, (size_t)(k1 - k0) * 8, cudaMemcpyHostToDevice, st));
+            rc = bz_crc_spans_dev(ctx, ctx->d_stream.as<u8>() + ooff[k0], d_se + 2 * k0, k1 - k0, (u32)max_span, ctx->d_crc.as<u32>() + k0);
+            if (rc) return rc;
+            BZ_CHECK(cudaStreamSynchronize(st));                // se is reused by the next sub-range
+            k0 = k1;
+        }
+        BZ_CHECK(cudaMemcpyAsync(crcs.data(), ctx->d_crc.p, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+        if (btotal) BZ_CHECK(cudaMemcpyAsync(out + total_out, ctx->d_stream.p, (size_t)btotal, cudaMemcpyDeviceToHost, st));
+        BZ_CHECK(cudaStreamSynchronize(st));
+        for (u32 k = 0; k < used; k++)
+            if (hlen[k] && crcs[k] != db[k].crc) { ctx->err = "decode: CRC mismatch in the block at bit " + std::to_string(starts[k]); return BZ2B200_E_CRC; }   // enforced, unlike decompress.rs:379-386
+        total_out += (size_t)btotal;
     }
-    if (combined != stored_combined) return BZ2B200_E_CRC;
-    BZ_CHECK(cudaMemcpyAsync(d_len, hlen.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-    BZ_CHECK(cudaMemcpyAsync(d_keys, hkey.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-    // ---- 3. inverse BWT ----
-    Batch B;
-    B.nblk = (int)nb; B.stride = stride; B.tiles = stride / BZ_TILE; B.max_n = max_n; B.nbits = 20; B.T = ctx->d_T.as<u8>();
-    B.len = d_len; B.total_n = total_n;
-    int rc = ibwt_batch(ctx, B, d_keys, ctx->d_bwt.as<u8>());
-    if (rc) return rc;
-    // ---- 4. inverse RLE1 + CRC ----
-    ctx->prof_begin(K_DEC_RLE1_COUNT, total_n); k_rle1_inv<0><<<nb, 256, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, d_olen, nullptr, nullptr); LAUNCH_OK();
-    std::vector<u64> olen(nb), ooff(nb);
-    BZ_CHECK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
-    BZ_CHECK(cudaStreamSynchronize(st));
-    u64 total = 0, max_span = 0;
-    std::vector<u32> se(2 * (size_t)nb);
-    for (u32 k = 0; k < nb; k++) { ooff[k] = total; total += olen[k]; max_span = std::max(max_span, olen[k]); }
-    if (total > 0xFFFFFF00ull) { ctx->err = "decode: output larger than 4 GiB is not supported in one call"; return BZ2B200_E_ARG; }
-    for (u32 k = 0; k < nb; k++) { se[2 * k] = (u32)ooff[k]; se[2 * k + 1] = (u32)(ooff[k] + olen[k]); }
-    *out_len = (size_t)total;
-    if (total > out_cap) return BZ2B200_E_CAP;
-    BZ_CHECK(ctx->d_stream.ensure((size_t)total + 64));
-    BZ_CHECK(cudaMemcpyAsync(d_ooff, ooff.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    BZ_CHECK(cudaMemcpyAsync(d_se, se.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin(K_DEC_RLE1_WRITE, total); k_rle1_inv<1><<<nb, 256, 0, st>>>(ctx->d_bwt.as<u8>(), d_len, stride, nullptr, d_ooff, ctx->d_stream.as<u8>()); LAUNCH_OK();
-    BZ_CHECK(ctx->d_crc.ensure((size_t)nb * 4));
-    rc = bz_crc_spans_dev(ctx, ctx->d_stream.as<u8>(), d_se, nb, (u32)max_span, ctx->d_crc.as<u32>());
-    if (rc) return rc;
-    std::vector<u32> crcs(nb);
-    BZ_CHECK(cudaMemcpyAsync(crcs.data(), ctx->d_crc.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    if (total) BZ_CHECK(cudaMemcpyAsync(out, ctx->d_stream.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-    BZ_CHECK(cudaStreamSynchronize(st));
-    for (u32 k = 0; k < nb; k++)
-        if (crcs[k] != db[k].crc) { ctx->err = "decode: CRC mismatch in block " + std::to_string(k); return BZ2B200_E_CRC; }   // enforced, unlike decompress.rs:379-386
+    *out_len = total_out;
     return BZ2B200_OK;
     BZ_API_CATCH
 }

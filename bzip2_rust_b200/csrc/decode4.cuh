@@ -27,7 +27,7 @@ struct DecTables {                     // per block, global memory
     u64 data_bit;                      // first bit of the symbol data
     u64 end_bit;                       // bit after the EOB code            (k_dec_bounds)
     u32 nsym, ngroups;                 // symbols incl. EOB, groups in use  (k_dec_bounds)
-    u32 nblock, pad;                   // decoded BWT string length          (k_dec_chunk_scan)
+    u32 nblock, pad;                   // decoded BWT string length (k_dec_chunk_scan); pad = the block's "randomised" bit
 };
 
 struct BitBuf {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const
     __shared__ u16 lut[6][1 << LUTBITS];
     __shared__ u8 seq[256];
     __shared__ int s_T, s_alpha, s_status;
-    __shared__ u32 s_G, s_crc, s_key;
+    __shared__ u32 s_G, s_crc, s_key, s_rand;
     __shared__ u64 s_data;
     const int lane = threadIdx.x;
     u8 *sel = sel_all + (size_t)b * sel_stride;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const
         s_status = 0;
         br.init(in, n, start_bits[b] + 48);
         { u32 hi16 = br.get(16); u32 lo16 = br.get(16); s_crc = (hi16 << 16) | lo16; }
-        if (br.get(1)) s_status = 1;                            // randomised blocks: not produced by this encoder
+        s_rand = br.get(1);                                     // legacy randomised block (decode.cu k_derandomize); encoders write 0 (compress_block.rs:41)
         s_key = br.get(24);
         u32 l1 = br.get(16);
         int nused = 0;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const
     for (int i = lane; i < 256; i += 32) o->seq[i] = seq[i];
     if (lane == 0) {
         o->T = (u32)T; o->alpha = (u32)alpha; o->G = s_G; o->status = (u32)s_status; o->crc = s_crc; o->key = s_key;
-        o->data_bit = s_data; o->end_bit = 0; o->nsym = 0; o->ngroups = 0; o->nblock = 0; o->pad = 0;
+        o->data_bit = s_data; o->end_bit = 0; o->nsym = 0; o->ngroups = 0; o->nblock = 0; o->pad = s_rand;
     }
 }
 

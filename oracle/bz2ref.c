@@ -995,7 +995,10 @@ static uint32_t rd_bits(bitrd *r, int k) {
     }
     return v;
 }
-int ref_decompress_stream(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+/* reference_semantics != 0: the reference's own decoder behaviour -- rle1_decode with its tail defect (rle1.rs:267-316,
+ * SURVEY D.6) and CRC mismatches that are only logged (decompress.rs:376-386, :394-402): they are counted, not fatal. */
+static int decompress_impl(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len, int reference_semantics,
+                           uint32_t *n_blocks, uint32_t *n_crc_mismatch) {
     bitrd r = { in, n, 0, 0 };
     if (rd_bits(&r, 8) != 'B' || rd_bits(&r, 8) != 'Z' || rd_bits(&r, 8) != 'h') return REF_ERR_FORMAT;
     int level = (int)rd_bits(&r, 8) - '0';
@@ -1084,13 +1087,27 @@ int ref_decompress_stream(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
         ref_bwt_decode(key, tt, nblk, blk);
         /* inverse RLE1 + crc */
         size_t before = o;
-        size_t got = ref_rle1_decode_standard(blk, nblk, out + o, cap - o);
+        size_t got = reference_semantics ? ref_rle1_decode_reference(blk, nblk, out + o, cap - o)
+                                         : ref_rle1_decode_standard(blk, nblk, out + o, cap - o);
         if (got == (size_t)-1) { rc = REF_ERR_CAP; break; }
         o += got;
-        if (ref_do_crc(0, out + before, got) != bcrc) { rc = REF_ERR_FORMAT; break; }
+        if (n_blocks) (*n_blocks)++;
+        if (ref_do_crc(0, out + before, got) != bcrc) {
+            if (!reference_semantics) { rc = REF_ERR_FORMAT; break; }
+            if (n_crc_mismatch) (*n_crc_mismatch)++;
+        }
         combined = ref_do_stream_crc(combined, bcrc);
     }
     free(tt); free(blk);
     *out_len = o;
     return rc;
+}
+int ref_decompress_stream(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+    return decompress_impl(in, n, out, cap, out_len, 0, NULL, NULL);
+}
+int ref_decompress_stream_reference(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len,
+                                    uint32_t *n_blocks, uint32_t *n_crc_mismatch) {
+    if (n_blocks) *n_blocks = 0;
+    if (n_crc_mismatch) *n_crc_mismatch = 0;
+    return decompress_impl(in, n, out, cap, out_len, 1, n_blocks, n_crc_mismatch);
 }

@@ -134,6 +134,10 @@ int ref_compress_stream(const uint8_t *in, size_t n, int level, int bwt_mode, in
 
 /* ---- decoder: standard bzip2 single-stream decode used as a cross-check of libbz2 ---- */
 int ref_decompress_stream(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+/* ---- decoder with the REFERENCE's semantics (decompress.rs:38-404): rle1_decode as written (rle1.rs:267-316, with the
+ * tail defect of SURVEY D.6) and CRC mismatches counted instead of enforced (the reference only logs them) ---- */
+int ref_decompress_stream_reference(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len,
+                                    uint32_t *n_blocks, uint32_t *n_crc_mismatch);
 
 #ifdef __cplusplus
 }

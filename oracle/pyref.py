@@ -275,6 +275,23 @@ def decompress_stream(data, cap=None):
     return buf.raw[:n.value]
 
 
+def decompress_stream_reference(data, cap=None):
+    """The reference's decoder semantics (decompress.rs:38-404 + rle1.rs:267-316) -> (bytes, blocks, blocks whose CRC the
+    reference would only have logged as wrong)."""
+    data = bytes(data)
+    cap = cap or max(len(data) * 60, 1 << 20)
+    buf = C.create_string_buffer(cap)
+    n = C.c_size_t()
+    nb, bad = C.c_uint32(), C.c_uint32()
+    L = lib()
+    L.ref_decompress_stream_reference.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    rc = L.ref_decompress_stream_reference(data, len(data), buf, cap, C.byref(n), C.byref(nb), C.byref(bad))
+    if rc != OK:
+        raise RuntimeError("ref_decompress_stream_reference failed: %d" % rc)
+    return buf.raw[:n.value], nb.value, bad.value
+
+
 class Packer:
     """BitPacker (bitpacker.rs:17-112) for the reference's own unit vectors."""
 
