@@ -29,7 +29,7 @@ _ERRNAMES = {E_ARG: "bad argument", E_CAP: "output buffer too small", E_CUDA: "C
 
 # every symbol include/bz2b200.h declares
 EXPORTS = [
-    "bz2b200_create", "bz2b200_destroy", "bz2b200_last_error", "bz2b200_version", "bz2b200_launch_count",
+    "bz2b200_create", "bz2b200_destroy", "bz2b200_trim", "bz2b200_last_error", "bz2b200_version", "bz2b200_launch_count",
     "bz2b200_compress_blocks", "bz2b200_compress_stream", "bz2b200_compress_stream_dev",
     "bz2b200_compress_bound", "bz2b200_stream_plan", "bz2b200_compress_range", "bz2b200_merge_streams",
     "bz2b200_crc32", "bz2b200_rle1_split", "bz2b200_bwt_encode", "bz2b200_bwt_encode_batch",
@@ -65,6 +65,7 @@ def load_library():
     L.bz2b200_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.bz2b200_destroy.argtypes = [vp]
     L.bz2b200_destroy.restype = None
+    L.bz2b200_trim.argtypes = [vp]
     L.bz2b200_last_error.argtypes = [vp]
     L.bz2b200_last_error.restype = C.c_char_p
     L.bz2b200_version.restype = C.c_char_p
@@ -149,6 +150,10 @@ class Engine:
     def _chk(self, rc):
         if rc != OK:
             raise Bz2B200Error(rc, self._L.bz2b200_last_error(self._h).decode())
+
+    def trim(self):
+        """Frees the device workspaces (grow-only otherwise)."""
+        self._chk(self._L.bz2b200_trim(self._h))
 
     @property
     def launches(self):

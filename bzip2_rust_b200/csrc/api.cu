@@ -3,8 +3,19 @@
 #include <string.h>
 #include <new>
 
+// every grow-only device buffer of a context
+static void release_device_buffers(bz2b200_ctx *c) {
+    DevBuf *all[] = {&c->d_T, &c->d_len, &c->d_crc, &c->d_SA, &c->d_SA2, &c->d_RANK, &c->d_F, &c->d_KEYA, &c->d_KEYB, &c->d_VALA,
+                     &c->d_VALB, &c->d_thist, &c->d_tagg, &c->d_cnt, &c->d_bwt, &c->d_key, &c->d_mtfstate, &c->d_chunkrec, &c->d_R,
+                     &c->d_sym, &c->d_m, &c->d_freq, &c->d_used, &c->d_agg2, &c->d_len6, &c->d_rfreq, &c->d_sel, &c->d_gbits,
+                     &c->d_hdr, &c->d_bitoff, &c->d_out, &c->d_outbits, &c->d_hmisc, &c->d_in, &c->d_runflag, &c->d_misc,
+                     &c->d_stream, &c->d_dec1, &c->d_dec2, &c->d_dec3};
+    for (DevBuf *b : all) b->release();
+}
+
 bz2b200_ctx::~bz2b200_ctx() {
     cudaSetDevice(device);
+    release_device_buffers(this);
     DevBuf *all[] = {&d_T, &d_len, &d_crc, &d_SA, &d_SA2, &d_RANK, &d_F, &d_KEYA, &d_KEYB, &d_VALA, &d_VALB,
                      &d_thist, &d_tagg, &d_cnt, &d_bwt, &d_key, &d_mtfstate, &d_chunkrec, &d_R, &d_sym, &d_m,
                      &d_freq, &d_used, &d_agg2, &d_len6, &d_rfreq, &d_sel, &d_gbits, &d_hdr, &d_bitoff, &d_out,
@@ -47,6 +58,15 @@ int bz2b200_create(int device, bz2b200_ctx **out) {
     BZ_API_CATCH
 }
 void bz2b200_destroy(bz2b200_ctx *ctx) { delete ctx; }
+int bz2b200_trim(bz2b200_ctx *ctx) {
+    if (!ctx) return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    cudaStreamSynchronize(ctx->stream);
+    release_device_buffers(ctx);
+    ctx->shard = ShardPlan();                                    // a pending shard plan pointed into the freed scans
+    return BZ2B200_OK;
+}
 const char *bz2b200_last_error(const bz2b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t bz2b200_launch_count(const bz2b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void bz2b200_set_timing(bz2b200_ctx *ctx, int on) { if (ctx) { ctx->timing = on != 0; ctx->prof_level = on; } }

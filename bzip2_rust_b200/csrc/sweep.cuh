@@ -47,13 +47,38 @@ __device__ __forceinline__ u32 ld_vol(const u32 *p) {
 }
 __device__ __forceinline__ void st_vol(u32 *p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+// ---- 1-D bulk copy global -> shared (TMA engine, `cp.async.bulk` + mbarrier; SASS: UBLKCP / SYNCS) ----
+// A full tile of a streaming pass (M_CARRY, M_LIST) is one contiguous, 16-byte aligned span: instead of 16 LDG per
+// thread, one thread posts a bulk copy into the staging buffer the pass needs anyway and the threads pick their
+// elements up with LDS once the mbarrier's transaction count is complete.
+#ifndef BZ_SWEEP_TMA
+#define BZ_SWEEP_TMA 0
+#endif
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 template <int MODE> struct Types { typedef u32 In; typedef u32 Stage; typedef u32 Out; };
 template <> struct Types<M_GATHER> { typedef u32 In; typedef u64 Stage; typedef u32 Out; };
 template <> struct Types<M_LIST> { typedef u64 In; typedef u64 Stage; typedef u64 Out; };
 
 template <int MODE, int IPT, bool FULL>
 __device__ __forceinline__ void tile_body(const Args &a, u32 b, u32 t, u32 base, u32 tile_n, u32 n, u32 *wh, u32 *toff,
-                                          u32 *ws, typename Types<MODE>::Stage *sbuf) {
+                                          u32 *ws, typename Types<MODE>::Stage *sbuf, u64 *bar) {
     typedef typename Types<MODE>::Stage S;
     typedef typename Types<MODE>::Out O;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -91,6 +116,11 @@ __device__ __forceinline__ void tile_body(const Args &a, u32 b, u32 t, u32 base,
             v[r] = (u32)v[r] | (d << 24);
             cp[r >> 2] |= c << (8 * (r & 3));
         }
+    } else if (BZ_SWEEP_TMA && FULL) {                          // the tile was posted as one bulk copy into sbuf (k_sweep)
+        mbar_wait(bar, 0);
+#pragma unroll
+        for (int r = 0; r < IPT; r++) v[r] = sbuf[e0 + r * 32];
+        // (the barrier before the scatter below also orders these reads before sbuf is overwritten)
     } else if (MODE == M_CARRY) {
         const u32 *in = (const u32 *)a.in + (size_t)b * a.stride + base;
 #pragma unroll
@@ -195,10 +225,14 @@ __global__ void __launch_bounds__(BZ_THREADS, min_ctas(MODE, IPT)) k_sweep(Args 
     __shared__ u32 wh[8 * 256];
     __shared__ u32 toff[256];
     __shared__ u32 ws[8];
-    __shared__ S sbuf[TILE];
+    __shared__ __align__(16) S sbuf[TILE];
+    __shared__ __align__(8) u64 s_bar;
     __shared__ u32 s_ticket;
     const int tid = threadIdx.x;
-    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    if (tid == 0) {
+        s_ticket = atomicAdd(a.ticket, 1u);
+        if (BZ_SWEEP_TMA && MODE != M_GATHER) mbar_init(&s_bar, 1);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) wh[k * 256 + tid] = 0;
     __syncthreads();
@@ -215,8 +249,13 @@ __global__ void __launch_bounds__(BZ_THREADS, min_ctas(MODE, IPT)) k_sweep(Args 
     if (base >= cnt) return;
     u32 n = a.len[b];
     u32 tile_n = min((u32)TILE, cnt - base);
-    if (tile_n == (u32)TILE) tile_body<MODE, IPT, true>(a, b, t, base, tile_n, n, wh, toff, ws, sbuf);
-    else tile_body<MODE, IPT, false>(a, b, t, base, tile_n, n, wh, toff, ws, sbuf);
+    if (tile_n == (u32)TILE) {
+        if (BZ_SWEEP_TMA && MODE != M_GATHER && tid == 0) {
+            typedef typename Types<MODE>::In I;
+            bulk_load(sbuf, (const I *)a.in + (size_t)b * a.stride + base, (u32)(TILE * sizeof(I)), &s_bar);
+        }
+        tile_body<MODE, IPT, true>(a, b, t, base, tile_n, n, wh, toff, ws, sbuf, &s_bar);
+    } else tile_body<MODE, IPT, false>(a, b, t, base, tile_n, n, wh, toff, ws, sbuf, &s_bar);
 }
 
 // tuning knobs (environment, read once): elements per thread of the initial / list passes, interleave group

@@ -47,6 +47,10 @@ enum {
 /* device < 0 selects the current CUDA device. */
 int  bz2b200_create(int device, bz2b200_ctx **out);
 void bz2b200_destroy(bz2b200_ctx *ctx);
+/* Frees the context's device workspaces (they are grow-only and sized by the largest call so far: about 45 bytes per
+ * input byte of one 256 MiB window plus the resident input / output of the host-buffer entry points).  The next call
+ * allocates what it needs again. */
+int  bz2b200_trim(bz2b200_ctx *ctx);
 const char *bz2b200_last_error(const bz2b200_ctx *ctx);
 const char *bz2b200_version(void);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */

@@ -703,8 +703,8 @@ static int node_desc_cmp(const void *pa, const void *pb, void *ctx) {
     if (key_less(a, b)) return 1;
     return 0;
 }
-void ref_improve_code_len(uint32_t *codes, const uint32_t *sym_weight, uint16_t eob,
-                          uint32_t *tie_events, uint32_t *retries) {   /* huffman_code_from_weights.rs:17-84 */
+static void improve_code_len(uint32_t *codes, const uint32_t *sym_weight, uint16_t eob,
+                             uint32_t *tie_events, uint32_t *retries, uint32_t *tie_unpinned) {   /* huffman_code_from_weights.rs:17-84 */
     int nsym = (int)eob + 1;
     uint32_t weight[258];
     for (int i = 0; i < nsym; i++) weight[i] = sym_weight[i] == 0 ? 256 : sym_weight[i] << 8;   /* :31 */
@@ -731,7 +731,14 @@ void ref_improve_code_len(uint32_t *codes, const uint32_t *sym_weight, uint16_t 
             while (pos > 0 && key_less(&nodes[order[pos - 1]], p)) { order[pos] = order[pos - 1]; pos--; }
             if (pos > 0 && tie_events) {
                 const hnode *q = &nodes[order[pos - 1]];
-                if (q->weight == p->weight && q->syms == p->syms) (*tie_events)++;
+                if (q->weight == p->weight && q->syms == p->syms) {
+                    (*tie_events)++;
+                    /* the reference sorts a vector of cnt + 1 nodes here (:49).  rustc 1.65's sort_unstable is an insertion
+                       sort up to 20 elements and repairs a nearly sorted input from 50 on (both keep the parent behind its
+                       equal); 21..49 elements go through an unstable partition: the order of the two equal nodes -- and with
+                       it the code lengths -- is not pinned by anything in this repository */
+                    if (tie_unpinned && cnt + 1 >= 21 && cnt + 1 <= 49) (*tie_unpinned)++;
+                }
             }
             order[pos] = (int16_t)nn;
             cnt++; nn++;
@@ -751,6 +758,11 @@ void ref_improve_code_len(uint32_t *codes, const uint32_t *sym_weight, uint16_t 
     }
 }
 
+void ref_improve_code_len(uint32_t *codes, const uint32_t *sym_weight, uint16_t eob,
+                          uint32_t *tie_events, uint32_t *retries) {
+    improve_code_len(codes, sym_weight, eob, tie_events, retries, NULL);
+}
+
 int ref_huf_encode(ref_bitpacker *bp, const uint16_t *rle2, uint32_t m, const uint32_t freq[256],
                    uint16_t eob, const uint16_t *symmap, int nmap, ref_huf_info *info) {   /* huffman.rs:79-468 */
     int T = m < 200 ? 2 : m < 600 ? 3 : m < 1200 ? 4 : m < 2400 ? 5 : 6;   /* :87-93 */
@@ -758,7 +770,7 @@ int ref_huf_encode(ref_bitpacker *bp, const uint16_t *rle2, uint32_t m, const ui
     ref_init_tables(freq, T, eob, tables);                          /* :96 */
     uint32_t G = m / 50 + (m % 50 != 0);                            /* :99 */
     uint8_t *sel = (uint8_t *)malloc(G ? G : 1);
-    uint32_t ties = 0, retries = 0;
+    uint32_t ties = 0, retries = 0, unpinned = 0;
     for (int iter = 0; iter < 4; iter++) {                          /* :114 */
         static __thread uint32_t rfreq[6][258];
         memset(rfreq, 0, sizeof rfreq);
@@ -770,7 +782,7 @@ int ref_huf_encode(ref_bitpacker *bp, const uint16_t *rle2, uint32_t m, const ui
             for (uint32_t i = a; i < b; i++) rfreq[bt][rle2[i]]++;  /* :165-167 */
             if (iter == 3) sel[g] = (uint8_t)bt;                    /* :171-173 */
         }
-        for (int t = 0; t < T; t++) ref_improve_code_len(tables[t], rfreq[t], eob, &ties, &retries);   /* :197-199 */
+        for (int t = 0; t < T; t++) improve_code_len(tables[t], rfreq[t], eob, &ties, &retries, &unpinned);   /* :197-199 */
     }
     for (int i = 0; i < nmap; i++) ref_bp_out16(bp, symmap[i]);     /* :209-212 */
     ref_bp_out24(bp, (3u << 24) | (uint32_t)T);                     /* :216 */
@@ -816,7 +828,7 @@ int ref_huf_encode(ref_bitpacker *bp, const uint16_t *rle2, uint32_t m, const ui
         for (uint32_t i = a; i < b; i++) ref_bp_out24(bp, codes[sel[g]][rle2[i]]);
     }
     if (info) {
-        info->table_count = T; info->selector_count = G; info->tie_events = ties; info->retries = retries;
+        info->table_count = T; info->selector_count = G; info->tie_events = ties; info->retries = retries; info->tie_unpinned = unpinned;
         for (int t = 0; t < 6; t++) for (int s = 0; s < 258; s++) info->lengths[t][s] = t < T && s < nsym ? (uint8_t)tables[t][s] : 0;
         if (info->selectors) memcpy(info->selectors, sel, G);
     }
@@ -968,7 +980,7 @@ int ref_compress_stream(const uint8_t *in, size_t n, int level, int bwt_mode, in
             stats->n_blocks++;
             if (b->info.path_used) stats->n_sais++; else stats->n_native++;
             stats->n_sais_divergent += (uint32_t)b->divergent;
-            stats->tie_events += b->info.huf.tie_events; stats->retries += b->info.huf.retries;
+            stats->tie_events += b->info.huf.tie_events; stats->retries += b->info.huf.retries; stats->tie_unpinned += b->info.huf.tie_unpinned;
         }
     }
     if (stats) stats->combined_crc = stream_crc;

@@ -92,6 +92,8 @@ typedef struct {
     uint8_t *selectors;         /* optional caller buffer of selector_count bytes (may be NULL) */
     uint32_t tie_events;        /* distinct nodes with equal (weight,syms) seen during tree builds */
     uint32_t retries;           /* depth>17 weight-halving retries */
+    uint32_t tie_unpinned;      /* tie events that happened while the node list held 21..49 entries: the only case whose
+                                   outcome depends on rustc 1.65's unstable partition */
 } ref_huf_info;
 
 /* bit packer (bitpacker.rs:17-112) */
@@ -126,6 +128,7 @@ typedef struct {
     uint32_t n_blocks, n_native, n_sais, n_sais_divergent;
     uint32_t tie_events, retries;
     uint32_t combined_crc;
+    uint32_t tie_unpinned;
 } ref_stream_stats;
 /* threads<=1: sequential.  Otherwise blocks are compressed by a pool of that many pthreads
  * (the reference uses rayon par_bridge, compress.rs:125-132). */

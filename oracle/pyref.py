@@ -24,7 +24,7 @@ def build(force=False):
 class HufInfo(C.Structure):
     _fields_ = [("table_count", C.c_int), ("selector_count", C.c_uint32),
                 ("lengths", (C.c_uint8 * 258) * 6), ("selectors", C.POINTER(C.c_uint8)),
-                ("tie_events", C.c_uint32), ("retries", C.c_uint32)]
+                ("tie_events", C.c_uint32), ("retries", C.c_uint32), ("tie_unpinned", C.c_uint32)]
 
 
 class BlockInfo(C.Structure):
@@ -34,7 +34,7 @@ class BlockInfo(C.Structure):
 class StreamStats(C.Structure):
     _fields_ = [("n_blocks", C.c_uint32), ("n_native", C.c_uint32), ("n_sais", C.c_uint32),
                 ("n_sais_divergent", C.c_uint32), ("tie_events", C.c_uint32), ("retries", C.c_uint32),
-                ("combined_crc", C.c_uint32)]
+                ("combined_crc", C.c_uint32), ("tie_unpinned", C.c_uint32)]
 
 
 class BitPacker(C.Structure):

@@ -77,12 +77,14 @@ def test_sweep1g_every_level_identical_and_round_trips(engine, ref):
 
 
 def test_corpus8g_identical_for_one_and_several_ranks(engine, ref):
-    """Config 4: 8 GB at level 9.  One GPU context, and the library's multi-rank scheduler with 2 and 8 ranks (32
-    windows dealt round robin), give the same bytes; those bytes are the oracle's."""
+    """Config 4: 8 GB at level 9.  One GPU context, and the library's multi-rank scheduler (30-32 windows dealt round
+    robin to 2 and 3 ranks that share the GPU, or to 2 and 8 distinct GPUs), give the same bytes; those bytes are the
+    oracle's."""
     n = 8_000_000_000
     data = corpus.corpus(n, 4, workers=WORKERS)
     got = engine.compress(data, 9)
-    for world in (2, 8):
+    engine.trim()                                               # ranks that share this GPU need the room (20 GB per rank)
+    for world in ((2, 8) if _ngpu() >= 8 else (2, 3)):
         m = bz.MultiEngine([r % max(1, _ngpu()) for r in range(world)])
         try:
             assert m.compress(data, 9) == got, "world %d differs from the single-context stream" % world
