@@ -5,13 +5,15 @@
 //   The input is cut into windows of at most 256 MiB (a multiple of N of them, dealt round robin: window k belongs to
 //   rank k mod N; one window per rank when the input is small).  Rank r (one host thread + one context per GPU),
 //   for each of its windows:
-//     1. uploads the window (+ look-ahead for its last block) in chunks; the RLE1 scan follows the chunks
+//     1. uploads the window (+ look-ahead for its last block) in chunks; the RLE1 scan follows the chunks.  The upload of
+//        the rank's NEXT window is posted first (second buffer, upload stream), so it runs under this window's kernels
 //     2. receives the first block start of the window from the window before it (a host atomic: the block chain
 //        s_{k+1} = e(s_k) of rle1.rs:245-264 is sequential, but a link only needs the scans around it),
 //        chains its own blocks and hands the next start to the next window BEFORE the heavy work
 //     3. compresses its blocks into one bit string (no stream header / footer)
 //     4. publishes its bit count; once the counts of the windows before it are known it shifts the string to its
-//        final bit phase on the device and copies it over its own PCIe link straight into the caller's buffer
+//        final bit phase on the device and copies it over its own PCIe link straight into the caller's buffer (download
+//        stream: the copy runs under the next window's kernels)
 //   the calling thread then ORs the seam bytes, folds the combined CRC in block order (crc.rs:25-27) and writes
 //   "BZh<level>" and the footer (bitwriter.rs:67-72, :103-114).
 // The output is the byte string a single bz2b200_compress_stream call produces, for any N.
@@ -25,8 +27,10 @@
 #include <string.h>
 #include <thread>
 
-int bz_shard_scan_upload(bz2b200_ctx *ctx, const u8 *h_src, u8 *d_win, size_t win_lo, size_t win_len, size_t n_total,
-                         int level, size_t chunk);
+int bz_shard_post_upload(bz2b200_ctx *ctx, const u8 *h_src, u8 *d_win, size_t win_len, size_t chunk,
+                         std::vector<cudaEvent_t> &evs);
+int bz_shard_scan_arriving(bz2b200_ctx *ctx, u8 *d_win, size_t win_lo, size_t win_len, size_t n_total, int level,
+                           size_t chunk, std::vector<cudaEvent_t> &evs);
 
 namespace {
 
@@ -43,7 +47,10 @@ struct MWin {                                // one input window
 struct MRank {
     bz2b200_ctx *ctx = nullptr;
     std::thread th;
-    DevBuf d_win, d_out, d_shift;
+    DevBuf d_win[2], d_out, d_shift[2];      // two windows in flight: one being compressed, the next one arriving
+    std::vector<cudaEvent_t> up_ev[2];       // upload progress of each window buffer
+    cudaEvent_t ev_shift = nullptr;
+    size_t posted_len[2] = {0, 0};
     int rc = 0;
     std::string err;
     size_t h2d = 0, d2h = 0;
@@ -95,27 +102,44 @@ int rank_fail(bz2b200_mctx *m, MRank &R, int rc, const char *what) {
 
 #define MCHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { R.rc = BZ2B200_E_CUDA; R.err = std::string(#call) + ": " + cudaGetErrorString(e_); m->abort.store(1); return R.rc; } } while (0)
 
-// one window on rank r
-int run_window(bz2b200_mctx *m, int r, size_t k) {
+const size_t LOOK0 = 4u << 20;               // look-ahead for the last block of a window, grown on demand
+inline size_t chunk_bytes() {
+    static const size_t c = [] { const char *e = getenv("BZ2B200_E2E_CHUNK_MB"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : v) << 20; }();
+    return c;
+}
+
+// posts the upload of window k into buffer `slot` of rank r (upload stream; returns at once)
+int post_window(bz2b200_mctx *m, int r, size_t k, int slot) {
+    MRank &R = *m->rk[r];
+    MWin &W = *m->win[k];
+    const size_t n = m->nbytes;
+    size_t win_len = std::min(n - W.lo, (W.hi - W.lo) + LOOK0);
+    MCHECK(R.d_win[slot].ensure(std::min(n - W.lo, (W.hi - W.lo) + (64u << 20)) + 64));
+    int rc = bz_shard_post_upload(R.ctx, m->in + W.lo, R.d_win[slot].as<u8>(), win_len, chunk_bytes(), R.up_ev[slot]);
+    if (rc) return rank_fail(m, R, rc, "upload");
+    R.posted_len[slot] = win_len;
+    R.h2d += win_len;
+    return BZ2B200_OK;
+}
+
+// one window on rank r; its upload has been posted into buffer `slot`; `i` = how many windows this rank did before
+int run_window(bz2b200_mctx *m, int r, size_t k, int slot, size_t i) {
     MRank &R = *m->rk[r];
     MWin &W = *m->win[k];
     bz2b200_ctx *ctx = R.ctx;
     const int level = m->level;
     const size_t n = m->nbytes, nwin = m->win.size();
     const size_t lo = W.lo, hi = W.hi;
-    static const size_t CHUNK = [] { const char *e = getenv("BZ2B200_E2E_CHUNK_MB"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : v) << 20; }();
     auto t0 = clk::now();
-    // ---- 1. upload + scan ----
-    size_t look = 4u << 20;                                     // look-ahead for the last block of the window, grown on demand
-    size_t win_len = std::min(n - lo, (hi - lo) + look);
+    // ---- 1. scan behind the upload ----
+    size_t look = LOOK0;
+    size_t win_len = R.posted_len[slot];
+    DevBuf &dwin = R.d_win[slot];
     size_t cap_out = bz2b200_compress_bound(hi - lo + (64u << 20));
-    MCHECK(R.d_win.ensure(std::min(n - lo, (hi - lo) + (64u << 20)) + 64));
     MCHECK(R.d_out.ensure(cap_out + 64));
-    MCHECK(R.d_shift.ensure(cap_out + 128));
     {
-        int rc = bz_shard_scan_upload(ctx, m->in + lo, R.d_win.as<u8>(), lo, win_len, n, level, CHUNK);
+        int rc = bz_shard_scan_arriving(ctx, dwin.as<u8>(), lo, win_len, n, level, chunk_bytes(), R.up_ev[slot]);
         if (rc) return rank_fail(m, R, rc, "scan");
-        R.h2d += win_len;
     }
     R.t_scan += ms_since(t0);
     // ---- 2. the chain ----
@@ -127,21 +151,21 @@ int run_window(bz2b200_mctx *m, int r, size_t k) {
     size_t nxt = (size_t)start;
     u32 nb = 0;
     for (;;) {
-        int rc = bz2b200_shard_plan_dev(ctx, R.d_win.as<u8>(), lo, win_len, n, level, (size_t)start, hi, &nxt, &nb);
+        int rc = bz2b200_shard_plan_dev(ctx, dwin.as<u8>(), lo, win_len, n, level, (size_t)start, hi, &nxt, &nb);
         if (rc == BZ2B200_OK) break;
         if (rc != BZ2B200_E_CAP || lo + win_len >= n) return rank_fail(m, R, rc, "plan");
         // a block of this window spans more input than the look-ahead (long runs): lengthen the window and plan again
         size_t new_len = std::min(n - lo, win_len + 8 * look);
         look *= 8;
-        if (R.d_win.cap < new_len + 64) {                       // keep what is already resident
+        if (dwin.cap < new_len + 64) {                          // keep what is already resident
             DevBuf bigger;
             MCHECK(bigger.ensure(std::min(n - lo, 2 * new_len) + 64));
-            MCHECK(cudaMemcpyAsync(bigger.p, R.d_win.p, win_len, cudaMemcpyDeviceToDevice, ctx->stream));
+            MCHECK(cudaMemcpyAsync(bigger.p, dwin.p, win_len, cudaMemcpyDeviceToDevice, ctx->stream));
             MCHECK(cudaStreamSynchronize(ctx->stream));
-            R.d_win.release();
-            R.d_win = bigger;
+            dwin.release();
+            dwin = bigger;
         }
-        MCHECK(cudaMemcpyAsync(R.d_win.as<u8>() + win_len, m->in + lo + win_len, new_len - win_len, cudaMemcpyHostToDevice, ctx->stream));
+        MCHECK(cudaMemcpyAsync(dwin.as<u8>() + win_len, m->in + lo + win_len, new_len - win_len, cudaMemcpyHostToDevice, ctx->stream));
         MCHECK(cudaStreamSynchronize(ctx->stream));
         R.h2d += new_len - win_len;
         win_len = new_len;
@@ -159,7 +183,7 @@ int run_window(bz2b200_mctx *m, int r, size_t k) {
     }
     W.bits_pub.store((long long)W.bits, std::memory_order_release);
     R.t_comp += ms_since(t3);
-    // ---- 4. final position, shift, download ----
+    // ---- 4. final position, shift, download (asynchronous: the copy runs under the next window) ----
     auto t4 = clk::now();
     u64 off = 32;
     for (size_t q = 0; q < k; q++) {
@@ -172,13 +196,17 @@ int run_window(bz2b200_mctx *m, int r, size_t k) {
         size_t nby = (size_t)((W.bits + phase + 7) / 8);
         W.byte_lo = (size_t)(off >> 3);
         if (W.byte_lo + nby + 16 > m->out_cap) { R.rc = BZ2B200_E_CAP; R.err = "output buffer too small"; m->abort.store(1); return R.rc; }
-        int rc = bz2b200_shift_bits_dev(ctx, R.d_out.as<u8>(), W.bits, phase, R.d_shift.as<u8>());
+        DevBuf &dsh = R.d_shift[i & 1];
+        if (i >= 2) MCHECK(cudaStreamSynchronize(ctx->s_down));  // the copy that last used this buffer (two windows ago)
+        MCHECK(dsh.ensure(cap_out + 128));
+        int rc = bz2b200_shift_bits_dev(ctx, R.d_out.as<u8>(), W.bits, phase, dsh.as<u8>());
         if (rc) return rank_fail(m, R, rc, "shift");
         W.seam = phase != 0;                                    // the first byte is shared with whatever precedes (window 0: phase 0)
         size_t skip = W.seam ? 1 : 0;
-        if (W.seam) MCHECK(cudaMemcpyAsync(&W.first_byte, R.d_shift.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
-        if (nby > skip) MCHECK(cudaMemcpyAsync(m->out + W.byte_lo + skip, R.d_shift.as<u8>() + skip, nby - skip, cudaMemcpyDeviceToHost, ctx->stream));
-        MCHECK(cudaStreamSynchronize(ctx->stream));
+        MCHECK(cudaEventRecord(R.ev_shift, ctx->stream));
+        MCHECK(cudaStreamWaitEvent(ctx->s_down, R.ev_shift, 0));
+        if (W.seam) MCHECK(cudaMemcpyAsync(&W.first_byte, dsh.p, 1, cudaMemcpyDeviceToHost, ctx->s_down));
+        if (nby > skip) MCHECK(cudaMemcpyAsync(m->out + W.byte_lo + skip, dsh.as<u8>() + skip, nby - skip, cudaMemcpyDeviceToHost, ctx->s_down));
         R.d2h += nby;
     }
     R.t_d2h += ms_since(t4);
@@ -190,10 +218,16 @@ int run_rank(bz2b200_mctx *m, int r) {
     R.rc = 0; R.err.clear(); R.h2d = R.d2h = 0; R.nblk = 0;
     R.t_scan = R.t_chain = R.t_comp = R.t_wait = R.t_d2h = 0;
     MCHECK(cudaSetDevice(R.ctx->device));
-    for (size_t k = (size_t)r; k < m->win.size(); k += (size_t)m->n) {
-        int rc = run_window(m, r, k);
+    if (!R.ev_shift) MCHECK(cudaEventCreateWithFlags(&R.ev_shift, cudaEventDisableTiming));
+    const size_t N = (size_t)m->n, nwin = m->win.size();
+    if ((size_t)r < nwin) { int rc = post_window(m, r, (size_t)r, 0); if (rc) return rc; }
+    size_t i = 0;
+    for (size_t k = (size_t)r; k < nwin; k += N, i++) {
+        if (k + N < nwin) { int rc = post_window(m, r, k + N, (int)((i + 1) & 1)); if (rc) return rc; }   // arrives under this window's kernels
+        int rc = run_window(m, r, k, (int)(i & 1), i);
         if (rc) return rc;
     }
+    if (R.ctx->s_down) MCHECK(cudaStreamSynchronize(R.ctx->s_down));
     return BZ2B200_OK;
 }
 
@@ -254,7 +288,12 @@ void bz2b200_destroy_multi(bz2b200_mctx *m) {
     for (auto &R : m->rk) {
         if (R->ctx) {
             cudaSetDevice(R->ctx->device);
-            R->d_win.release(); R->d_out.release(); R->d_shift.release();
+            for (int q = 0; q < 2; q++) {
+                R->d_win[q].release(); R->d_shift[q].release();
+                for (cudaEvent_t e : R->up_ev[q]) cudaEventDestroy(e);
+            }
+            R->d_out.release();
+            if (R->ev_shift) cudaEventDestroy(R->ev_shift);
             bz2b200_destroy(R->ctx);
         }
     }
@@ -282,9 +321,15 @@ int bz2b200_compress_stream_multi(bz2b200_mctx *m, const uint8_t *in, size_t n, 
     m->in = in; m->nbytes = n; m->level = level; m->out = out; m->out_cap = out_cap;
     m->abort.store(0);
     {   // windows: a multiple of n_devices, at most 256 MiB each, whole 4 KiB pages
-        const size_t WMAX = 256u << 20;
+        // Two windows per rank when four or more GPUs upload at once and a window still holds 32 MiB: the uploads then share
+        // the host's memory bandwidth (measured: 100 MB per GPU take 2.0 ms on 2 GPUs, 4.4 ms on 8) and the second window's
+        // upload hides under the first one's compression; a window costs about 1 ms of fixed work, which is more than
+        // the hidden copy on 1-2 GPUs (measured on 2 GPUs: 16.3 ms with one window per rank, 17.0 with two, 18.3 with three).
+        const size_t WMAX = 256u << 20, WMIN = 32u << 20;
         size_t per_rank = (n + (size_t)m->n - 1) / (size_t)m->n;
-        size_t nwin = (size_t)m->n * ((per_rank + WMAX - 1) / WMAX);
+        size_t per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (per_rank >= 2 * WMIN && m->n >= 4) ? 2 : 1);
+        if (const char *e = getenv("BZ2B200_MULTI_WINDOWS")) { int v = atoi(e); if (v >= 1) per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (size_t)v); }
+        size_t nwin = (size_t)m->n * per;
         size_t wsz = (((n + nwin - 1) / nwin) + 4095) & ~(size_t)4095;
         m->win.clear();
         for (size_t lo = 0; lo < n; lo += wsz) {

@@ -35,12 +35,13 @@ int do_scan(bz2b200_ctx *ctx, ShardPlan &P, const u8 *d_win, size_t win_lo, size
 }
 }  // namespace
 
-// Phase 1 for a window that still sits in HOST memory (multi.cu): the window is uploaded in chunks on the context's
-// upload stream and the scan kernels follow chunk by chunk (bz_rle1_window, "arrival").
-int bz_shard_scan_upload(bz2b200_ctx *ctx, const u8 *h_src, u8 *d_win, size_t win_lo, size_t win_len, size_t n_total,
-                         int level, size_t chunk) {
-    if (!ctx || !h_src || !d_win || level < 1 || level > 9 || win_lo + win_len > n_total || win_len > 0xFFFFFF00ull || win_len == 0)
-        return BZ2B200_E_ARG;
+// Phase 1 for a window that still sits in HOST memory (multi.cu), in two steps so that the upload of a rank's NEXT window
+// can run under the compression of the current one:
+//   bz_shard_post_upload   the window is copied in chunks on the context's upload stream, one event per chunk
+//   bz_shard_scan_arriving the scan kernels follow the chunks as they land (bz_rle1_window, "arrival")
+int bz_shard_post_upload(bz2b200_ctx *ctx, const u8 *h_src, u8 *d_win, size_t win_len, size_t chunk,
+                         std::vector<cudaEvent_t> &evs) {
+    if (!ctx || !h_src || !d_win || win_len == 0 || chunk == 0) return BZ2B200_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
     if (!ctx->s_up) {
@@ -48,25 +49,36 @@ int bz_shard_scan_upload(bz2b200_ctx *ctx, const u8 *h_src, u8 *d_win, size_t wi
         BZ_CHECK(cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
     }
     size_t nchunks = (win_len + chunk - 1) / chunk;
-    while (ctx->up_ev.size() < nchunks) {
+    while (evs.size() < nchunks) {
         cudaEvent_t e;
         BZ_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ctx->up_ev.push_back(e);
+        evs.push_back(e);
     }
-    std::vector<cudaEvent_t> evs(ctx->up_ev.begin(), ctx->up_ev.begin() + nchunks);
     for (size_t i = 0; i < nchunks; i++) {
         size_t off = i * chunk, len = std::min(chunk, win_len - off);
         BZ_CHECK(cudaMemcpyAsync(d_win + off, h_src + off, len, cudaMemcpyHostToDevice, ctx->s_up));
         BZ_CHECK(cudaEventRecord(evs[i], ctx->s_up));
     }
+    return BZ2B200_OK;
+}
+
+int bz_shard_scan_arriving(bz2b200_ctx *ctx, u8 *d_win, size_t win_lo, size_t win_len, size_t n_total, int level,
+                           size_t chunk, std::vector<cudaEvent_t> &evs) {
+    if (!ctx || !d_win || level < 1 || level > 9 || win_lo + win_len > n_total || win_len > 0xFFFFFF00ull || win_len == 0)
+        return BZ2B200_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BZ2B200_E_CUDA;
+    size_t nchunks = (win_len + chunk - 1) / chunk;
+    if (evs.size() < nchunks) return BZ2B200_E_ARG;
+    std::vector<cudaEvent_t> mine(evs.begin(), evs.begin() + nchunks);
     Arrival arr;
-    arr.ev = &evs; arr.chunk = chunk; arr.win_off = 0; arr.waited = 0;
+    arr.ev = &mine; arr.chunk = chunk; arr.win_off = 0; arr.waited = 0;
     ctx->arrival = &arr;
     int rc = do_scan(ctx, ctx->shard, d_win, win_lo, win_len, n_total, level);
     ctx->arrival = nullptr;
     if (rc) { cudaStreamSynchronize(ctx->s_up); return rc; }
     // everything the later phases read must be resident: the compute stream waits for the last chunk
-    while (arr.waited < nchunks) { BZ_CHECK(cudaStreamWaitEvent(ctx->stream, evs[arr.waited], 0)); arr.waited++; }
+    while (arr.waited < nchunks) { BZ_CHECK(cudaStreamWaitEvent(ctx->stream, mine[arr.waited], 0)); arr.waited++; }
     return BZ2B200_OK;
 }
 

@@ -43,6 +43,19 @@ def test_worlds_produce_the_single_gpu_stream(engine, data80, world):
     assert bz2.decompress(got) == data80.tobytes()
 
 
+def test_several_windows_per_rank(engine, data80, monkeypatch):
+    """A rank works through its windows one after the other while the next window's upload and the previous window's
+    download are in flight (two buffers each): 3 and 5 windows per rank must give the same bytes."""
+    want = engine.compress(data80, 9)
+    for per, world in ((3, 2), (5, 3)):
+        monkeypatch.setenv("BZ2B200_MULTI_WINDOWS", str(per))
+        m = bz.MultiEngine(_devices(world))
+        try:
+            assert m.compress(data80, 9) == want, (per, world)
+        finally:
+            m.close()
+
+
 def test_multi_equals_oracle_on_two_text_segments(engine, ref):
     data = np.concatenate([corpus.text(20_000_000, 2), corpus.text(20_000_000, 3)])
     m = bz.MultiEngine(_devices(2))
