@@ -16,11 +16,6 @@ static void release_device_buffers(bz2b200_ctx *c) {
 bz2b200_ctx::~bz2b200_ctx() {
     cudaSetDevice(device);
     release_device_buffers(this);
-    DevBuf *all[] = {&d_T, &d_len, &d_crc, &d_SA, &d_SA2, &d_RANK, &d_F, &d_KEYA, &d_KEYB, &d_VALA, &d_VALB,
-                     &d_thist, &d_tagg, &d_cnt, &d_bwt, &d_key, &d_mtfstate, &d_chunkrec, &d_R, &d_sym, &d_m,
-                     &d_freq, &d_used, &d_agg2, &d_len6, &d_rfreq, &d_sel, &d_gbits, &d_hdr, &d_bitoff, &d_out,
-                     &d_outbits, &d_hmisc, &d_in, &d_runflag, &d_misc, &d_stream, &d_dec1, &d_dec2, &d_dec3};
-    for (DevBuf *b : all) b->release();
     h_stage.release(); h_small.release(); h_out.release();
     for (int i = 0; i < 8; i++) if (ev[i]) cudaEventDestroy(ev[i]);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);

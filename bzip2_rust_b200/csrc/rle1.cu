@@ -20,6 +20,8 @@
 // text array consumed by the BWT stage, and the block CRCs are computed as a polynomial in
 // X = x^(8*PIECE) over end-aligned pieces (leading zero bytes do not change a zero-init CRC).
 #include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -254,6 +256,7 @@ struct ChainArgs {
     u32 max_out;      // largest RLE1 block the batch stride can hold
     u32 s0;           // first block start (window relative)
     u32 stop_at;      // stop the chain at the first block start >= stop_at (shard end), window relative
+    u32 out_w;        // OUT[W]: RLE1 bytes of the whole window (read once by the kernel)
     u32 off_from;     // EOF bookkeeping: a group starting at/after this position since the last refill puts the
                       // reference's `remaining` counter one high (rle1.rs:207) -- see DESIGN.md "EOF corner"
     BlockRec *rec; u32 *nrec; u32 *consumed;
@@ -339,31 +342,67 @@ __device__ __forceinline__ int plan_block(const ChainArgs &a, u32 s, BlockRec &r
         long long off = (long long)r.out_re - (long long)a.OUT[re];
         long long target = (long long)B - 1 - off;              // first x >= re with OUT[x] >= target
         u32 x1;
-        if ((long long)a.OUT[W] < target) x1 = W + 1;           // never reached inside the window
+        u32 lq_m1 = NOQ, lq_p3 = NOQ;                           // LASTQ[x1 - 1], LASTQ[min(x1 + 3, W - 1)] when the probe below saw them
+        bool have_m1 = false, have_p3 = false;
+        if ((long long)a.out_w < target) x1 = W + 1;            // never reached inside the window
         else {
             // run-free data emits one byte per input byte, so the answer is usually re + (bytes still to emit):
             // verify that guess with two independent loads before falling back to the search
             long long need = target - (long long)a.OUT[re];
             u64 guess = (u64)re + (u64)(need > 0 ? need : 0);
-            if (need <= 0) x1 = re;
-            else if (guess <= W && (long long)a.OUT[guess] >= target && (long long)a.OUT[guess - 1] < target) x1 = (u32)guess;
+            bool solved = false;
+            if (need <= 0) { x1 = re; solved = true; }
             else if (COOP) {
-                // a few runs per block move the answer some bytes away from the guess: search +-512 positions first
-                // (two probe rounds, and that neighbourhood was prefetched) before the whole window (five rounds)
-                u64 g64 = guess > W ? W : guess;
-                u32 lo_w = g64 > (u64)re + 512 ? (u32)g64 - 512u : re;
-                u32 hi_w = g64 + 512 < (u64)W ? (u32)g64 + 512u : W;
-                if ((long long)a.OUT[lo_w] < target && (long long)a.OUT[hi_w] >= target) x1 = warp_lower_bound(a.OUT, lo_w, hi_w, target);
-                else x1 = warp_lower_bound(a.OUT, re, W, target);
-            } else return PLAN_SEARCH;
+                // One probe by the whole warp: lane l looks at position guess - 15 + l of OUT and LASTQ.  A few runs per block
+                // move the answer a few bytes off the guess, so this usually finds it -- the first position at or above the
+                // target whose predecessor is below it -- together with the two LASTQ entries the group test below needs,
+                // in ONE round trip instead of four (the chain is a sequence of dependent L2 / DRAM accesses).
+                const int lane = threadIdx.x & 31;
+                const long long wlo = (long long)guess - 15;
+                const long long p = wlo + lane;
+                const bool inb = p >= (long long)re && p <= (long long)W;
+                const u32 o = inb ? a.OUT[p] : 0u;
+                const u32 lqv = (p >= 0 && p < (long long)W) ? a.LASTQ[p] : NOQ;
+                const unsigned bal = __ballot_sync(0xffffffffu, inb && (long long)o >= target);
+                const unsigned inm = __ballot_sync(0xffffffffu, inb);
+                if (bal) {
+                    const int f = __ffs(bal) - 1;
+                    const long long xp = wlo + f;
+                    if (xp == (long long)re || (f > 0 && ((inm >> (f - 1)) & 1u))) {      // its predecessor was probed and is below
+                        x1 = (u32)xp; solved = true;
+                        if (f >= 1) { lq_m1 = __shfl_sync(0xffffffffu, lqv, f - 1); have_m1 = true; }
+                        const long long hl = (long long)min(x1 + 3, W - 1) - wlo;
+                        if (hl >= 0 && hl < 32) { lq_p3 = __shfl_sync(0xffffffffu, lqv, (int)hl); have_p3 = true; }
+                    }
+                }
+            }
+            if (!solved) {
+                if (guess <= W && (long long)a.OUT[guess] >= target && (long long)a.OUT[guess - 1] < target) x1 = (u32)guess;
+                else if (COOP) {
+                    // search +-512 positions first (two probe rounds, and that neighbourhood was prefetched) before the whole
+                    // window (five rounds)
+                    u64 g64 = guess > W ? W : guess;
+                    u32 lo_w = g64 > (u64)re + 512 ? (u32)g64 - 512u : re;
+                    u32 hi_w = g64 + 512 < (u64)W ? (u32)g64 + 512u : W;
+                    if ((long long)a.OUT[lo_w] < target && (long long)a.OUT[hi_w] >= target) x1 = warp_lower_bound(a.OUT, lo_w, hi_w, target);
+                    else x1 = warp_lower_bound(a.OUT, re, W, target);
+                } else {                                        // one thread on its own (k_rle_tab_fill): plain binary search
+                    u32 lo = re, hi = W;                        // OUT[W] >= target was checked above
+                    while (lo < hi) {
+                        u32 mid = lo + (hi - lo) / 2;
+                        if ((long long)a.OUT[mid] >= target) hi = mid; else lo = mid + 1;
+                    }
+                    x1 = lo;
+                }
+            }
         }
         u32 gl = NOQ;                                           // start of the last taken global group
         if (x1 <= W) {
             // the only group that can sit exactly at the limit starts in [x1, x1+3]
             u32 hiq = min(x1 + 3, W - 1);
             // both look-ups depend only on x1: issue them together (each is a DRAM/L2 round trip on the serial chain)
-            u32 q1_pre = x1 < W ? a.LASTQ[hiq] : NOQ;
-            u32 qp_pre = x1 > re ? a.LASTQ[x1 - 1] : NOQ;
+            u32 q1_pre = x1 < W ? (have_p3 ? lq_p3 : a.LASTQ[hiq]) : NOQ;
+            u32 qp_pre = x1 > re ? (have_m1 ? lq_m1 : a.LASTQ[x1 - 1]) : NOQ;
             if (x1 < W) {
                 u32 q1 = q1_pre;
                 if (q1 != NOQ && q1 >= x1 && q1 >= re && (long long)a.OUT[q1] + off == (long long)B - 1) {
@@ -425,38 +464,129 @@ __device__ __forceinline__ int plan_block(const ChainArgs &a, u32 s, BlockRec &r
     return PLAN_OK;
 }
 
-// The chain s_{k+1} = e(s_k) is sequential and a block costs ~7 dependent loads from arrays far larger than the L2
-// (~6 us of DRAM latency per block).  The next block starts within a few hundred bytes of s + (span of this block),
-// so while lane-uniform code plans block k the lanes prefetch that neighbourhood of RS / OUT / LASTQ / x for block
-// k+1 (its start, and its end one span further).  (Planning 32 guessed starts at once was tried: real text has a
-// few runs per block, spans differ by some bytes, and only lane 0's guess is ever confirmed.)
+// The chain s_{k+1} = e(s_k) is sequential, and one warp needs ~3 us per link (a few dependent L2 / DRAM accesses plus
+// ~600 dependent instructions with nobody to hide their latency behind): 0.36 ms for the 112 blocks of 100 MB, paid once
+// per GPU and in SERIES across the GPUs of a multi-GPU call.  So the links are evaluated SPECULATIVELY in parallel:
+// a block emits B .. B+5 bytes, hence the k-th block after a known start s begins where the global output offset OUT is
+// within [OUT[s] + k (B - 10), OUT[s] + k (B + 15)] (the slack covers runs that are re-chunked at a block start).
+//   k_rle_tab_bounds  the candidate window of every block of a segment of 128 blocks (three binary searches per block)
+//   k_rle_tab_fill    one THREAD per candidate start evaluates the full link e(s) (plan_block, ~10^5 of them per segment)
+//   k_rle_chain       walks the segment: a link is one table look-up; a start outside its window (long runs) falls back
+//                     to the cooperative evaluation, so the tables only ever make the walk faster, never different
+// The running state (blocks planned, next start, finished) lives in device memory, so segment after segment is launched
+// without any host round trip.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(32) k_rle_chain(ChainArgs a) {
+constexpr u32 CH_SEG = 128;                                      // blocks per speculative segment
+__host__ __device__ inline u32 tab_cap(u32 k) { return 32u * k + 256u; }                        // candidates kept for link k (k >= 1)
+__host__ __device__ inline u32 tab_off(u32 k) { return 16u * k * (k - 1u) + 256u * (k - 1u); }  // sum of tab_cap(1 .. k-1)
+constexpr u32 TAB_ENTRIES = 16u * (CH_SEG + 1) * CH_SEG + 256u * CH_SEG;                        // tab_off(CH_SEG + 1)
+constexpr u32 REC_BAD = 0xFFFFFFFFu;
+
+struct ChainState { u32 nb, s, done, hits; };                    // blocks planned so far, start of the next block, chain finished, table hits
+
+struct TabArgs {
+    ChainArgs a;
+    ChainState *state;
+    u32 *tlo, *tcnt;          // [CH_SEG + 1] candidate window of link k of the current segment
+    BlockRec *tab;            // [TAB_ENTRIES]
+};
+
+__device__ u32 lower_bound_out(const u32 *OUT, u32 lo, u32 hi, u64 target) {     // first x in [lo, hi] with OUT[x] >= target, hi + 1 if none
+    if ((u64)OUT[hi] < target) return hi + 1;
+    while (lo < hi) {
+        u32 mid = lo + (hi - lo) / 2;
+        if ((u64)OUT[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) k_rle_tab_bounds(TabArgs t) {
+    const u32 k = blockIdx.x * 128 + threadIdx.x + 1;            // link k: the k-th block after the segment's first one
+    if (k > CH_SEG) return;
+    const ChainState st = *t.state;
+    t.tcnt[k] = 0;
+    if (st.done || st.s >= t.a.W) return;
+    const u32 W = t.a.W, B = t.a.B;
+    const u64 base = t.a.OUT[st.s];
+    u32 lo = lower_bound_out(t.a.OUT, st.s, W, base + (u64)k * (B - 10));
+    if (lo > W) return;
+    u32 hi = lower_bound_out(t.a.OUT, lo, W, base + (u64)k * (B + 15) + 1);
+    if (hi > W) hi = W;
+    u32 cap = tab_cap(k);
+    if (hi - lo + 1 > cap) {                                     // keep the part around the expected offset (blocks average B + 2.5 bytes)
+        u32 c = lower_bound_out(t.a.OUT, lo, hi, base + (u64)k * B + (5ull * k) / 2);
+        u32 from = c > lo + cap / 2 ? c - cap / 2 : lo;
+        if (from + cap - 1 > hi) from = hi + 1 - cap;
+        lo = from; hi = from + cap - 1;
+    }
+    t.tlo[k] = lo; t.tcnt[k] = hi - lo + 1;
+}
+
+__global__ void __launch_bounds__(128) k_rle_tab_fill(TabArgs t) {
+    const u32 k = blockIdx.y + 1;
+    const u32 j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= t.tcnt[k]) return;
+    const u32 s = t.tlo[k] + j;
+    BlockRec r;
+    r.out_len = REC_BAD;
+    if (s < t.a.W) {
+        ChainArgs a = t.a;
+        a.out_w = a.OUT[a.W];
+        if (plan_block<false>(a, s, r) != PLAN_OK) r.out_len = REC_BAD;
+    }
+    t.tab[tab_off(k) + j] = r;
+}
+
+__global__ void __launch_bounds__(32) k_rle_chain(TabArgs t) {
     // all 32 lanes run the same control flow (every value is warp-uniform); lane 0 writes the results
+    ChainArgs a = t.a;
     const int lane = threadIdx.x;
     const u32 W = a.W;
-    u32 s = a.s0, nb = 0;                                       // s0: a true block start inside the scanned window
+    ChainState st = *t.state;
+    if (st.done) return;
+    a.out_w = a.OUT[W];
+    u32 s = st.s, nb = st.nb, hits = st.hits;
     u32 span = a.B;
-    while (s < W && s < a.stop_at && nb < a.max_blocks) {
-        {   // lanes 0..15: around the next block's start; lanes 16..31: around its end.  128-byte lines of u32 = 32 entries.
-            u64 c = (u64)s + (u64)span * (lane < 16 ? 1u : 2u);
-            long long p = (long long)c - 1024 + (long long)(lane & 15) * 128;       // 2 KB window of positions
-            if (p >= 0 && (u64)p + 32 < (u64)W) {
-                prefetch_l2(a.OUT + p); prefetch_l2(a.OUT + p + 32); prefetch_l2(a.OUT + p + 64); prefetch_l2(a.OUT + p + 96);
-                prefetch_l2(a.LASTQ + p); prefetch_l2(a.LASTQ + p + 32); prefetch_l2(a.LASTQ + p + 64); prefetch_l2(a.LASTQ + p + 96);
-                prefetch_l2(a.RS + p); prefetch_l2(a.RS + p + 32); prefetch_l2(a.RS + p + 64); prefetch_l2(a.RS + p + 96);
-                prefetch_l2(a.x + p);
+    bool finished = true;                                        // left the loop for good (not because the segment is over)
+    for (u32 k = 0;; k++) {
+        if (!(s < W && s < a.stop_at && nb < a.max_blocks)) break;
+        if (k > CH_SEG) { finished = false; break; }             // the next segment continues from here
+        BlockRec r;
+        bool have = false;
+        if (t.tab && k >= 1) {
+            u32 lo = t.tlo[k], cnt = t.tcnt[k];
+            if (s >= lo && s - lo < cnt) {
+                const uint4 *src = (const uint4 *)(t.tab + tab_off(k) + (s - lo));
+                uint4 q0 = src[0], q1 = src[1];
+                r.s = q0.x; r.e = q0.y; r.re = q0.z; r.g_last = q0.w; r.out_re = q1.x; r.out_g = q1.y; r.out_len = q1.z; r.last = q1.w;
+                have = r.out_len != REC_BAD && r.s == s;
+                hits += have ? 1u : 0u;
             }
         }
-        BlockRec r;
-        if (plan_block<true>(a, s, r) != PLAN_OK) break;
+        if (!have) {
+            {   // lanes 0..15: around the next block's start; lanes 16..31: around its end.  128-byte lines of u32 = 32 entries.
+                u64 c = (u64)s + (u64)span * (lane < 16 ? 1u : 2u);
+                long long p = (long long)c - 1024 + (long long)(lane & 15) * 128;       // 2 KB window of positions
+                if (p >= 0 && (u64)p + 32 < (u64)W) {
+                    prefetch_l2(a.OUT + p); prefetch_l2(a.OUT + p + 32); prefetch_l2(a.OUT + p + 64); prefetch_l2(a.OUT + p + 96);
+                    prefetch_l2(a.LASTQ + p); prefetch_l2(a.LASTQ + p + 32); prefetch_l2(a.LASTQ + p + 64); prefetch_l2(a.LASTQ + p + 96);
+                    prefetch_l2(a.RS + p); prefetch_l2(a.RS + p + 32); prefetch_l2(a.RS + p + 64); prefetch_l2(a.RS + p + 96);
+                    prefetch_l2(a.x + p);
+                }
+            }
+            if (plan_block<true>(a, s, r) != PLAN_OK) break;
+        }
         if (lane == 0) a.rec[nb] = r;
         nb++;
         span = r.e - s;
         s = r.e;
     }
-    if (lane == 0) { *a.nrec = nb; *a.consumed = s; }
+    if (lane == 0) {
+        ChainState o; o.nb = nb; o.s = s; o.done = finished ? 1u : 0u; o.hits = hits;
+        *t.state = o;
+        *a.nrec = nb; *a.consumed = s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -636,7 +766,32 @@ int bz_rle1_window(bz2b200_ctx *ctx, const u8 *d_x, u32 W, int level, bool is_eo
     a.max_blocks = max_blocks; a.max_out = max_n; a.off_from = off_from; a.stop_at = stop_at; a.s0 = s0;
     a.rec = rec; a.nrec = d_small; a.consumed = d_small + 1;
     if (plan_only && skip_chain) { *nblocks = 0; *consumed = 0; return BZ2B200_OK; }   // scan-only call
-    if (!skip_chain) { ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(a); LAUNCH_OK(); }
+    if (!skip_chain) {
+        // segment after segment of 1 + CH_SEG blocks: candidate windows, speculative links, walk -- no host round trip in between
+        static const bool use_tab = [] { const char *e = getenv("BZ2B200_CHAIN_TABLES"); return !e || atoi(e) != 0; }();
+        BZ_CHECK(ctx->d_F.ensure(sizeof(ChainState) + 2 * (size_t)(CH_SEG + 1) * 4 + (size_t)TAB_ENTRIES * sizeof(BlockRec) + 256));
+        TabArgs t;
+        t.a = a;
+        t.state = ctx->d_F.as<ChainState>();
+        t.tlo = (u32 *)(t.state + 1);
+        t.tcnt = t.tlo + (CH_SEG + 1);
+        t.tab = use_tab ? (BlockRec *)(((uintptr_t)(t.tcnt + (CH_SEG + 1)) + 15) & ~(uintptr_t)15) : nullptr;
+        ChainState st0; st0.nb = 0; st0.s = s0; st0.done = 0; st0.hits = 0;
+        BZ_CHECK(cudaMemcpyAsync(t.state, &st0, sizeof st0, cudaMemcpyHostToDevice, st));
+        // upper bound of the blocks this call can plan: B output bytes need at least 4/5 B input bytes (runs of exactly four
+        // grow to five bytes)
+        u64 span_in = (u64)W - (u64)(s0 < W ? s0 : W);
+        u32 kmax = (u32)std::min<u64>(max_blocks, span_in / ((u64)Bsz * 4 / 5 - 8) + 2);
+        u32 nseg = (kmax + CH_SEG) / (CH_SEG + 1);
+        for (u32 g = 0; g < nseg; g++) {
+            if (use_tab) {
+                ctx->prof_begin(K_RLE_CHAIN, 0); k_rle_tab_bounds<<<(CH_SEG + 127) / 128, 128, 0, st>>>(t); LAUNCH_OK();
+                dim3 gf((tab_cap(CH_SEG) + 127) / 128, CH_SEG);
+                ctx->prof_begin(K_RLE_CHAIN, 0); k_rle_tab_fill<<<gf, 128, 0, st>>>(t); LAUNCH_OK();
+            }
+            ctx->prof_begin(K_RLE_CHAIN, (u64)max_blocks * 32); k_rle_chain<<<1, 32, 0, st>>>(t); LAUNCH_OK();
+        }
+    }
     u32 *hs = ctx->h_small.as<u32>();
     BZ_CHECK(cudaMemcpyAsync(hs, d_small, 8, cudaMemcpyDeviceToHost, st));
     BZ_CHECK(cudaStreamSynchronize(st));
