@@ -39,6 +39,7 @@ EXPORTS = [
     "bz2b200_shard_plan_dev", "bz2b200_shard_compress_dev", "bz2b200_shift_bits_dev", "bz2b200_shard_scan_dev",
     "bz2b200_create_multi", "bz2b200_destroy_multi", "bz2b200_last_error_multi", "bz2b200_multi_devices",
     "bz2b200_multi_context", "bz2b200_compress_stream_multi", "bz2b200_multi_stats",
+    "bz2b200_zstream_open", "bz2b200_zstream_write", "bz2b200_zstream_close",
 ]
 
 
@@ -49,6 +50,7 @@ class Bz2B200Error(RuntimeError):
 
 
 _lib = None
+SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)     # bz2b200_sink
 
 
 def load_library():
@@ -115,6 +117,9 @@ def load_library():
     L.bz2b200_multi_context.restype = vp
     L.bz2b200_compress_stream_multi.argtypes = [vp, u8p, C.c_size_t, C.c_int, u8p, C.c_size_t, szp]
     L.bz2b200_multi_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 8)]
+    L.bz2b200_zstream_open.argtypes = [vp, C.c_int, SINK, vp, C.POINTER(vp)]
+    L.bz2b200_zstream_write.argtypes = [vp, u8p, C.c_size_t]
+    L.bz2b200_zstream_close.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -381,6 +386,63 @@ class Engine:
         self._L.bz2b200_get_timing(self._h, C.byref(ms))
         names = ["rle1_crc_split", "bwt", "mtf_rle2", "huffman", "bitpack", "total"]
         return {k: float(ms[i]) for i, k in enumerate(names)}
+
+
+class ZStream:
+    """Streaming compression (bz2b200_zstream_*): write() input in pieces; finished .bz2 bytes go to `out.write`.
+
+        with ZStream(engine, fileobj, level=9) as z:
+            for piece in pieces: z.write(piece)
+    """
+
+    def __init__(self, engine, out, level=9):
+        self._L = engine._L
+        self._eng = engine
+        self._out = out
+        self._err = None
+
+        def sink(_user, data, n):
+            try:
+                self._out.write(C.string_at(data, n))
+                return 0
+            except Exception as e:          # an exception must not unwind through the C library
+                self._err = e
+                return 1
+
+        self._cb = SINK(sink)               # keep the callback object alive as long as the stream
+        h = C.c_void_p()
+        rc = self._L.bz2b200_zstream_open(engine._h, level, self._cb, None, C.byref(h))
+        if rc != OK:
+            if self._err is not None:
+                raise self._err             # the sink failed on the stream header
+            raise Bz2B200Error(rc, "bz2b200_zstream_open")
+        self._h = h
+        self.total_in = self.total_out = 0
+
+    def write(self, data):
+        a = _np_u8(data)
+        rc = self._L.bz2b200_zstream_write(self._h, a.ctypes.data, a.size)
+        if rc != OK:
+            raise Bz2B200Error(rc, self._L.bz2b200_last_error(self._eng._h).decode())
+
+    def close(self):
+        if self._h is None:
+            return
+        ti, to = C.c_uint64(), C.c_uint64()
+        rc = self._L.bz2b200_zstream_close(self._h, C.byref(ti), C.byref(to))
+        self._h = None
+        self.total_in, self.total_out = ti.value, to.value
+        if self._err is not None:
+            raise self._err
+        if rc != OK:
+            raise Bz2B200Error(rc, self._L.bz2b200_last_error(self._eng._h).decode())
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 class MultiEngine:

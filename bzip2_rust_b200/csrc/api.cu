@@ -27,7 +27,7 @@ bz2b200_ctx::~bz2b200_ctx() {
 
 extern "C" {
 
-const char *bz2b200_version(void) { return "bz2b200 0.1 (sm_100a)"; }
+const char *bz2b200_version(void) { return "bz2b200 0.2 (sm_100a)"; }
 
 int bz2b200_create(int device, bz2b200_ctx **out) {
     BZ_API_TRY

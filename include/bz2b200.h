@@ -116,6 +116,22 @@ int bz2b200_merge_streams(int level, int nparts, const uint8_t *const *part, con
                           const uint32_t *const *part_crcs, const uint32_t *part_ncrc,
                           uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* ---- seam: compress (compress.rs:40-136) as a pipeline: the input arrives in pieces ------------------------- */
+/* The reference never holds the file: RLE1Block refills block_size bytes at a time (src/tools/rle1.rs:63-85) while
+ * rayon workers compress and a writer thread appends finished blocks (compress.rs:74-122).  A zstream does the same
+ * with the GPU: bz2b200_zstream_write copies the caller's bytes into page-locked staging (two windows of 64 MiB); a
+ * worker thread uploads a full window behind the unconsumed tail of the previous one, runs all block kernels and hands
+ * the finished .bz2 bytes to `sink` (called on the worker thread, in stream order; a non-zero return aborts), so the
+ * caller's reading overlaps upload, kernels, download and the sink's writing.  bz2b200_zstream_close compresses what is
+ * left, writes the footer and frees the stream (also after an error).  The sink receives exactly the bytes
+ * bz2b200_compress_stream produces for the concatenated input.  The context must not be used by other threads while a
+ * zstream is open on it (calls are serialised, so they would only wait). */
+typedef struct bz2b200_zstream bz2b200_zstream;
+typedef int (*bz2b200_sink)(void *user, const uint8_t *data, size_t n);
+int bz2b200_zstream_open(bz2b200_ctx *ctx, int level, bz2b200_sink sink, void *user, bz2b200_zstream **out);
+int bz2b200_zstream_write(bz2b200_zstream *z, const uint8_t *data, size_t n);
+int bz2b200_zstream_close(bz2b200_zstream *z, uint64_t *total_in, uint64_t *total_out);
+
 /* ---- seam: compress (src/compression/compress.rs:40-136) on SEVERAL GPUs of one process -------------------- */
 /* The reference fans blocks out to rayon workers (compress.rs:125-132) and a writer thread puts them back in
  * order (compress.rs:74-122).  A multi context owns n_devices single-GPU contexts and one host thread per GPU

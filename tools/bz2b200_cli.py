@@ -53,13 +53,35 @@ def main(argv=None):
     files = a.files or ["-"]
     for name in files:
         try:
-            data = sys.stdin.buffer.read() if name == "-" else open(name, "rb").read()
             if mode == "z":
-                out = eng.compress(data, level)
+                # pipelined: the file is read in pieces while earlier pieces are uploaded, compressed and written
                 oname = name + ".bz2"
-            else:
-                out = eng.decompress(data)
-                oname = name[:-4] if name.endswith(".bz2") else name + ".out"
+                to_stdout = a.stdout or name == "-"
+                if not to_stdout and os.path.exists(oname) and not a.force:
+                    sys.stderr.write("bz2b200: output file %s already exists (use -f)\n" % oname)
+                    rc = 1
+                    continue
+                src = sys.stdin.buffer if name == "-" else open(name, "rb")
+                dst = sys.stdout.buffer if to_stdout else open(oname, "wb")
+                try:
+                    with bz.ZStream(eng, dst, level) as z:
+                        while True:
+                            piece = src.read(16 << 20)
+                            if not piece:
+                                break
+                            z.write(piece)
+                finally:
+                    if src is not sys.stdin.buffer:
+                        src.close()
+                    if dst is not sys.stdout.buffer:
+                        dst.close()                       # the input file stays (reference: "ALWAYS KEEPS")
+                if a.verbose and not a.quiet:
+                    sys.stderr.write("  %s: %d -> %d bytes (%.3f:1)\n" % (name, z.total_in, z.total_out,
+                                                                         z.total_in / max(1, z.total_out)))
+                continue
+            data = sys.stdin.buffer.read() if name == "-" else open(name, "rb").read()
+            out = eng.decompress(data)
+            oname = name[:-4] if name.endswith(".bz2") else name + ".out"
             if mode == "t":
                 if not a.quiet:
                     sys.stderr.write("%s: ok\n" % name)

@@ -1,6 +1,6 @@
 """Runs the BASELINE.json configs on one B200 and prints one JSON object per config.
 
-    python tools/run_configs.py [text100m] [rep256m] [sweep] [decode]
+    python tools/run_configs.py [text100m] [markov100m] [rep256m] [sweep] [big] [decode]
 
 Throughput = input bytes / wall time of bz2b200_compress_stream_dev (input + output resident in HBM), best of 3
 after one warm-up.  Parity: byte identity against the CPU oracle on a leading sample (the oracle needs seconds
@@ -34,7 +34,7 @@ def timed_compress(eng, d_in, n, level, d_out, cap, reps=3):
     return best, ln
 
 
-def run(name, data, level, eng, L, oracle_sample=4_000_000, verify=True):
+def run(name, data, level, eng, L, oracle_sample=4_000_000, verify=True, ref_paths=False):
     n = data.size
     d_in = torch.from_numpy(data).cuda()
     cap = int(L.bz2b200_compress_bound(n))
@@ -44,7 +44,13 @@ def run(name, data, level, eng, L, oracle_sample=4_000_000, verify=True):
     st = eng.timing()
     bw = eng.bwt_stats()
     res = {"config": name, "level": level, "input_bytes": n, "compressed_bytes": ln, "MBps": n / 1e6 / dt,
-           "ms": dt * 1e3, "stage_ms": st, "bwt_rounds_last_batch": int(bw["rounds"])}
+           "ms": dt * 1e3, "stage_ms": st, "bwt_rounds_last_batch": int(bw["rounds"]),
+           "bwt_list_sum_per_n_last_batch": round(bw["list_sum"] / max(1, min(n, 272 << 20)), 3),
+           "bwt_big_path_share": round(bw["big_sum"] / max(1, bw["list_sum"]), 4)}
+    if ref_paths:
+        # blocks native / sais-valid / sais-divergent (the oracle's bug-for-bug EXACT mode on the flagged blocks)
+        import bench
+        res["ref_path"] = bench.ref_path_accounting(eng, data[:min(n, 64_000_000)], level, limit=24)
     if verify:
         stream = d_out[:ln].cpu().numpy().tobytes()
         raw = data.tobytes()
@@ -65,17 +71,20 @@ def run(name, data, level, eng, L, oracle_sample=4_000_000, verify=True):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"text100m", "rep256m", "sweep", "decode"}
+    which = set(sys.argv[1:]) or {"text100m", "markov100m", "rep256m", "sweep", "decode"}
     eng = bz.Engine(0)
     L = bz.load_library()
+    wk = corpus.default_workers()
     if "text100m" in which:
-        run("text100m", corpus.text(100_000_000, 2), 9, eng, L)
+        run("text100m", corpus.text(100_000_000, 2), 9, eng, L, ref_paths=True)
+    if "markov100m" in which:
+        run("markov100m", corpus.markov(100_000_000, 6, workers=wk), 9, eng, L, ref_paths=True)
     if "rep256m" in which:
-        run("rep256m", corpus.repetitive(256_000_000, 3), 9, eng, L)
+        run("rep256m", corpus.rep_segments(256_000_000, 3, workers=wk), 9, eng, L, ref_paths=True)
     if "sweep" in which:
-        data = corpus.mixed(1_000_000_000 if "big" in which else 256_000_000, 5)
+        data = corpus.mixed(1_000_000_000 if "big" in which else 256_000_000, 5, workers=wk)
         for level in range(1, 10):
-            run("sweep_mixed", data, level, eng, L, verify=(level in (1, 9)))
+            run("sweep_mixed", data, level, eng, L, verify=(level in (1, 9)), ref_paths=(level == 9))
     if "decode" in which:
         import ctypes as C
         data = corpus.text(100_000_000, 2)
