@@ -398,6 +398,7 @@ def _main(args, real_stdout):
     launches = eng.launches - launches0
     kstats = eng.kernel_stats()
     stage = eng.timing()
+    bst_timed = eng.bwt_stats()                                # of the last timed step (later calls overwrite the per-batch fields)
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
@@ -520,8 +521,10 @@ def _main(args, real_stdout):
         # blocks (since the engine was created) that the reference's path selector (bwt_sort.rs:29) would have sent to its
         # SA-IS fallback, counted on the device: 0 means the reference's output is well defined for the whole workload
         "ref_path": ref_path,
-        "bwt": {"rounds": int(bst["rounds"]), "list_sum_per_n": round(bst["list_sum"] / max(1, total if world == 1 else per), 4),
-                "big_path_share": round(bst["big_sum"] / max(1, bst["list_sum"]), 4)},
+        # prefix doubling of the last timed step: rounds after the 8-byte sort, unresolved-list entries summed over the rounds
+        # per input byte, and the part of them that took the global (BIG group) path instead of the shared-memory refinement
+        "bwt": {"rounds": int(bst_timed["rounds"]), "list_sum_per_n": round(bst_timed["list_sum"] / max(1, per), 4),
+                "big_path_share": round(bst_timed["big_sum"] / max(1, bst_timed["list_sum"]), 4)},
         "compressed_bytes": int(clen),
     }
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
