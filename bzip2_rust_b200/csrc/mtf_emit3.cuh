@@ -17,6 +17,124 @@
 // rank 0 <=> byte equals its predecessor, so zero runs, RUNA/RUNB digits and output offsets inside the step are
 // plain lane arithmetic plus one warp scan.
 
+// The register copy of the list positions covers only what a block uses: with nused <= 32 * SPL byte values a lane owns
+// the SPL used values of slots [SPL * lane, SPL * lane + SPL) (compact, ascending) instead of the 8 byte values
+// [8 * lane, 8 * lane + 8) -- text has 30-100 distinct bytes, so the per-distinct-value update of the inner loop works
+// on 1, 1 or 2 words instead of 4.  SPL = 8 keeps the value-indexed 8-byte load / store (binary data: every value used).
+template <int SPL>
+__device__ __forceinline__ void mtf_emit_chunk(const u8 *L, u16 *so, u32 a, u32 e, int nused, const u8 *sused, u8 *sposw,
+                                               u32 front, u32 z, u32 o, u32 *sfreq, u32 &runa, u32 &runb, u32 &o_out, u32 &z_out) {
+    const int lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1u;
+    constexpr int NW = SPL == 8 ? 4 : (SPL + 1) / 2;            // position words per lane (two 16-bit lanes each)
+    const u32 M2 = 0x00ff00ffu;
+    u32 prev_last = front;                                      // the list front stands in for "previous byte"
+    u64 *pos8 = (u64 *)sposw + lane;                            // SPL == 8: values 8*lane .. 8*lane+7
+    u32 myv[SPL == 8 ? 1 : SPL];                                // SPL < 8: the byte values this lane owns (256 = none)
+    if (SPL < 8) {
+#pragma unroll
+        for (int q = 0; q < (SPL == 8 ? 1 : SPL); q++) {
+            int slot = lane * SPL + q;
+            myv[q] = slot < nused ? (u32)sused[slot] : 256u;
+        }
+    }
+    for (u32 i0 = a; i0 < e; i0 += 32) {
+        const int cntk = (int)min(32u, e - i0);
+        const bool valid = lane < cntk;
+        const u32 ch = valid ? (u32)L[i0 + lane] : (0x100u | (u32)lane);
+        u32 pb = __shfl_up_sync(0xffffffffu, ch, 1);
+        if (lane == 0) pb = prev_last;
+        const bool nz = valid && ch != pb;                  // rank != 0  <=>  differs from the previous byte
+        const u32 nzmask = __ballot_sync(0xffffffffu, nz);
+        prev_last = __shfl_sync(0xffffffffu, ch, cntk - 1);
+        if (nzmask == 0) { z += (u32)cntk; continue; }      // the whole step continues one run
+        const u32 peers = __match_any_sync(0xffffffffu, ch);
+        const u32 r0 = valid ? (u32)sposw[ch] : 0u;
+        const u32 earlier = peers & lt;
+        const bool has_j = earlier != 0;
+        // lanes strictly between the previous occurrence (or the step start) and this lane
+        const u32 wmask = has_j ? (lt & ~((2u << (31 - __clz(earlier))) - 1u)) : lt;
+        const bool is_last = valid && (peers >> lane) == 1u;    // no later lane holds the same byte
+        u32 firstmask = __ballot_sync(0xffffffffu, valid && !has_j);
+        const u32 lastmask = __ballot_sync(0xffffffffu, is_last);
+        // positions as words of two 16-bit lanes: cm = 255 - pos (compare operand), np = new position
+        u32 np[NW], cm[NW];
+        if (SPL == 8) {
+            const u64 op = *pos8;
+            np[0] = (u32)op & M2; np[1 % NW] = ((u32)op >> 8) & M2; np[2 % NW] = (u32)(op >> 32) & M2; np[3 % NW] = ((u32)(op >> 32) >> 8) & M2;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                u32 lo = myv[(2 * j) % (SPL == 8 ? 1 : SPL)] < 256u ? (u32)sposw[myv[(2 * j) % (SPL == 8 ? 1 : SPL)]] : 255u;
+                u32 hi = 255u;
+                if (2 * j + 1 < SPL) hi = myv[(2 * j + 1) % (SPL == 8 ? 1 : SPL)] < 256u ? (u32)sposw[myv[(2 * j + 1) % (SPL == 8 ? 1 : SPL)]] : 255u;
+                np[j] = lo | (hi << 16);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NW; q++) cm[q] = M2 - np[q];
+        const u32 thr = has_j ? 0u : r0 + 1u;               // "pos[v] > pos[c]" only matters when c has no earlier occurrence
+        u32 rank = has_j ? 0u : r0;
+#pragma unroll 1
+        while (firstmask) {                                 // one iteration per distinct value of the step
+            int k = __ffs(firstmask) - 1;
+            firstmask &= firstmask - 1;
+            u32 P = __shfl_sync(0xffffffffu, peers, k);
+            u32 rv = __shfl_sync(0xffffffffu, r0, k);
+            if ((P & wmask) != 0 && rv >= thr) rank++;
+            const u32 rv2 = rv * 0x00010001u;
+#pragma unroll
+            for (int q = 0; q < NW; q++) np[q] += ((cm[q] + rv2) >> 8) & 0x00010001u;    // +1 where pos < rv: rv's value moves ahead
+        }
+        if (SPL == 8) {
+            u32 lo = (np[0] & M2) | ((np[1 % NW] & M2) << 8), hi = (np[2 % NW] & M2) | ((np[3 % NW] & M2) << 8);
+            *pos8 = ((u64)hi << 32) | lo;
+        } else {
+#pragma unroll
+            for (int q = 0; q < (SPL == 8 ? 1 : SPL); q++)
+                if (myv[q] < 256u) sposw[myv[q]] = (u8)(np[q >> 1] >> (16 * (q & 1)));
+        }
+        __syncwarp();
+        if (is_last) sposw[ch] = (u8)__popc(lastmask & ~lt & ~(1u << lane));
+        __syncwarp();
+        // ---- zero runs and output slots ----
+        u32 below = nzmask & lt;
+        u32 zrun = 0, nd = 0;
+        if (nz) {
+            zrun = below ? (u32)(lane - (31 - __clz(below)) - 1) : z + (u32)lane;
+            nd = zrun ? (u32)(31 - __clz(zrun + 1)) : 0u;
+        }
+        u32 emits = nz ? nd + 1u : 0u;
+        u32 inc = emits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        if (nz) {
+            u32 off = o + inc - emits;
+            u32 zz = zrun + 1;
+#pragma unroll 1
+            for (u32 q = 0; q < nd; q++) so[off + q] = (u16)((zz >> q) & 1u);     // RUNA = 0, RUNB = 1 (rle2_mtf.rs:68-100)
+            u32 ones = __popc(zz & ((1u << nd) - 1u));
+            runb += ones; runa += nd - ones;
+            so[off + nd] = (u16)(rank + 1);
+        }
+        {   // freq[rank] (rle2_mtf.rs:104), one shared-memory atomic per distinct rank of the step
+            u32 key = nz ? rank : 0xffffu;
+            u32 same = __match_any_sync(0xffffffffu, key);
+            if (nz && (same & lt) == 0) atomicAdd(&sfreq[rank], (u32)__popc(same));
+        }
+        o += total;
+        z = (u32)(cntk - 1 - (31 - __clz(nzmask)));        // zeros after the last non-zero rank of the step
+    }
+    o_out = o; z_out = z;
+}
+
+#ifndef BZ_MTF_COMPACT
+#define BZ_MTF_COMPACT 1
+#endif
 __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit3(const u8 *Lall, const u32 *len, const u32 *usedbits,
                                                           const int *pm, const u32 *zbefore, const u32 *ooff,
                                                           const u32 *m_in, u16 *sym, u32 *freq, u32 stride,
@@ -61,89 +179,13 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit3(const u8 *Lall, const 
             if (rk == 0) s_front[w] = (u32)s;
         }
         __syncwarp();
-        const u32 lt = (1u << lane) - 1u;
         u32 z = zbefore[(size_t)b * nch_stride + c];            // pending zero run
         u32 o = ooff[(size_t)b * nch_stride + c];               // next output slot
-        u32 prev_last = s_front[w];                             // the list front stands in for "previous byte"
-        u64 *pos8 = (u64 *)spos[w] + lane;                      // values 8*lane .. 8*lane+7
-        for (u32 i0 = a; i0 < e; i0 += 32) {
-            const int cntk = (int)min(32u, e - i0);
-            const bool valid = lane < cntk;
-            const u32 ch = valid ? (u32)L[i0 + lane] : (0x100u | (u32)lane);
-            u32 pb = __shfl_up_sync(0xffffffffu, ch, 1);
-            if (lane == 0) pb = prev_last;
-            const bool nz = valid && ch != pb;                  // rank != 0  <=>  differs from the previous byte
-            const u32 nzmask = __ballot_sync(0xffffffffu, nz);
-            prev_last = __shfl_sync(0xffffffffu, ch, cntk - 1);
-            if (nzmask == 0) { z += (u32)cntk; continue; }      // the whole step continues one run
-            const u32 peers = __match_any_sync(0xffffffffu, ch);
-            const u32 r0 = valid ? (u32)spos[w][ch] : 0u;
-            const u32 earlier = peers & lt;
-            const bool has_j = earlier != 0;
-            // lanes strictly between the previous occurrence (or the step start) and this lane
-            const u32 wmask = has_j ? (lt & ~((2u << (31 - __clz(earlier))) - 1u)) : lt;
-            const bool is_last = valid && (peers >> lane) == 1u;    // no later lane holds the same byte
-            u32 firstmask = __ballot_sync(0xffffffffu, valid && !has_j);
-            const u32 lastmask = __ballot_sync(0xffffffffu, is_last);
-            // 8 positions as four words of two 16-bit lanes: cm = 255 - pos (compare operand), np = new position
-            const u64 op = *pos8;
-            const u32 M2 = 0x00ff00ffu;
-            u32 np[4], cm[4];
-            np[0] = (u32)op & M2; np[1] = ((u32)op >> 8) & M2; np[2] = (u32)(op >> 32) & M2; np[3] = ((u32)(op >> 32) >> 8) & M2;
-#pragma unroll
-            for (int q = 0; q < 4; q++) cm[q] = M2 - np[q];
-            const u32 thr = has_j ? 0u : r0 + 1u;               // "pos[v] > pos[c]" only matters when c has no earlier occurrence
-            u32 rank = has_j ? 0u : r0;
-#pragma unroll 1
-            while (firstmask) {                                 // one iteration per distinct value of the step
-                int k = __ffs(firstmask) - 1;
-                firstmask &= firstmask - 1;
-                u32 P = __shfl_sync(0xffffffffu, peers, k);
-                u32 rv = __shfl_sync(0xffffffffu, r0, k);
-                if ((P & wmask) != 0 && rv >= thr) rank++;
-                const u32 rv2 = rv * 0x00010001u;
-#pragma unroll
-                for (int q = 0; q < 4; q++) np[q] += ((cm[q] + rv2) >> 8) & 0x00010001u;    // +1 where pos < rv: rv's value moves ahead
-            }
-            {
-                u32 lo = (np[0] & M2) | ((np[1] & M2) << 8), hi = (np[2] & M2) | ((np[3] & M2) << 8);
-                *pos8 = ((u64)hi << 32) | lo;
-            }
-            __syncwarp();
-            if (is_last) spos[w][ch] = (u8)__popc(lastmask & ~lt & ~(1u << lane));
-            __syncwarp();
-            // ---- zero runs and output slots ----
-            u32 below = nzmask & lt;
-            u32 zrun = 0, nd = 0;
-            if (nz) {
-                zrun = below ? (u32)(lane - (31 - __clz(below)) - 1) : z + (u32)lane;
-                nd = zrun ? (u32)(31 - __clz(zrun + 1)) : 0u;
-            }
-            u32 emits = nz ? nd + 1u : 0u;
-            u32 inc = emits;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u32 t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            u32 total = __shfl_sync(0xffffffffu, inc, 31);
-            if (nz) {
-                u32 off = o + inc - emits;
-                u32 zz = zrun + 1;
-#pragma unroll 1
-                for (u32 q = 0; q < nd; q++) so[off + q] = (u16)((zz >> q) & 1u);     // RUNA = 0, RUNB = 1 (rle2_mtf.rs:68-100)
-                u32 ones = __popc(zz & ((1u << nd) - 1u));
-                runb += ones; runa += nd - ones;
-                so[off + nd] = (u16)(rank + 1);
-            }
-            {   // freq[rank] (rle2_mtf.rs:104), one shared-memory atomic per distinct rank of the step
-                u32 key = nz ? rank : 0xffffu;
-                u32 same = __match_any_sync(0xffffffffu, key);
-                if (nz && (same & lt) == 0) atomicAdd(&sfreq[rank], (u32)__popc(same));
-            }
-            o += total;
-            z = (u32)(cntk - 1 - (31 - __clz(nzmask)));        // zeros after the last non-zero rank of the step
-        }
+        const u32 front = s_front[w];
+        if (BZ_MTF_COMPACT && nused <= 32) mtf_emit_chunk<1>(L, so, a, e, nused, sused, spos[w], front, z, o, sfreq, runa, runb, o, z);
+        else if (BZ_MTF_COMPACT && nused <= 64) mtf_emit_chunk<2>(L, so, a, e, nused, sused, spos[w], front, z, o, sfreq, runa, runb, o, z);
+        else if (BZ_MTF_COMPACT && nused <= 128) mtf_emit_chunk<4>(L, so, a, e, nused, sused, spos[w], front, z, o, sfreq, runa, runb, o, z);
+        else mtf_emit_chunk<8>(L, so, a, e, nused, sused, spos[w], front, z, o, sfreq, runa, runb, o, z);
         if (lane == 0) {
             bool next_nz = (e >= n) ? true : (L[e] != L[e - 1]);
             if (z && next_nz) {

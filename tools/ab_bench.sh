@@ -6,6 +6,6 @@ for so in bzip2_rust_b200/libbz2b200.so gpurun_ab/*.so; do
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k={x[0]:x[1] for x in d['kernels']}
-print('$so $BZ2B200_REFINE_GROUP', 'value %.0f e2e %.0f dev_ms %.2f bwt %.2f' % (d['value'], d['e2e']['value'], d['device_ms_per_step'], d['stage_ms']['bwt']), {n:k.get(n) for n in ('k_refine_local','k_init_ranks','k_list_key','k_sweep_list','k_list_refine')})
+print('$so $BZ2B200_REFINE_GROUP', 'value %.0f e2e %.0f dev_ms %.2f bwt %.2f' % (d['value'], d['e2e']['value'], d['device_ms_per_step'], d['stage_ms']['bwt']), {n:k.get(n) for n in ('k_sweep_gather','k_sweep_carry','k_byte_hist','k_key8_table','k_init_ranks','k_refine_local','k_mtf_emit','k_bwt_out')})
 "
 done
