@@ -18,6 +18,8 @@ bz2b200_ctx::~bz2b200_ctx() {
     release_device_buffers(this);
     h_stage.release(); h_small.release(); h_out.release();
     for (int i = 0; i < 8; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < 2; i++) if (ev_dec[i]) cudaEventDestroy(ev_dec[i]);
+    if (s_hi) cudaStreamDestroy(s_hi);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : up_ev) cudaEventDestroy(e);
     if (s_up) cudaStreamDestroy(s_up);

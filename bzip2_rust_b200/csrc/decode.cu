@@ -6,9 +6,10 @@
 // The reference decodes one block after another on one thread; blocks are independent once their
 // start bits are known, so:
 //   k_dec_find_magic  every bit offset is tested for the 48-bit block / footer magic
-//   decode4.cuh       entropy decode, parallel inside a block: header -> tables, a lengths-only walk for the
-//                     bit offset of every 50-symbol group, one thread per group for the symbols, inverse MTF +
-//                     RUNA/RUNB by chunks whose start lists come from composing per-chunk permutations
+//   decode4.cuh       entropy decode, parallel inside a block: header -> tables, the bit offset of every 50-symbol
+//                     group (decode_bounds.cuh: jump tables over all bit offsets, then 7 look-ups per group), one
+//                     thread per group for the symbols, inverse MTF + RUNA/RUNB by chunks whose start lists come
+//                     from composing per-chunk permutations
 //   inverse BWT       stable counting sort of rows by byte = one pass of the BWT stage's radix kernels
 //                     (P[j] = row of the j-th smallest byte), then the n-step pointer chase of
 //                     bwt_decode is cut into ~n/256 segments at splitter rows: k_ibwt_chase measures
@@ -22,6 +23,7 @@
 #include "radix.cuh"
 #include <algorithm>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 int bz_crc_spans_dev(bz2b200_ctx *ctx, const u8 *d_x, const u32 *d_se /* [nb][2] */, u32 nb, u32 max_span,
@@ -31,7 +33,10 @@ namespace {
 
 constexpr u64 MAGIC_BLOCK = 0x314159265359ull;
 constexpr u64 MAGIC_END = 0x177245385090ull;
-constexpr int SPLIT = 256;               // inverse BWT: one splitter row every SPLIT rows
+#ifndef BZ_IBWT_SPLIT
+#define BZ_IBWT_SPLIT 64
+#endif
+constexpr int SPLIT = BZ_IBWT_SPLIT;     // inverse BWT: one splitter row every SPLIT rows
 
 __device__ __forceinline__ u64 load_be64(const u8 *p, size_t n, size_t byte) {
     u64 v = 0;
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(256) k_ibwt_write(const u32 *P, const u8 *L, c
     } while (!is_split(row, key) && off < n);
 }
 
-#include "decode4.cuh"       // entropy decode: header, group boundaries, symbols, chunked inverse MTF
+#include "decode4.cuh"        // entropy decode: header, symbols, chunked inverse MTF
+#include "decode_bounds.cuh"  // ... and the group boundaries (jump tables + walk)
 #include "decode_rle1.cuh"   // k_rle1_inv
 
 }  // namespace
@@ -139,7 +145,7 @@ static int ibwt_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_keys, u8 *d
     BZ_CHECK(ctx->d_SA.ensure(ne * 4));
     BZ_CHECK(ctx->d_thist.ensure((size_t)B.nblk * rtiles * 256 * 4));
     u32 sstride = B.stride / SPLIT + 2;
-    u32 vstride = B.stride + sstride;
+    u32 vstride = B.stride + sstride;   // a periodic block walks its (short) cycle many times: up to n visits
     BZ_CHECK(ctx->d_dec2.ensure((size_t)B.nblk * sstride * 8 + (size_t)B.nblk * vstride * 8 + (size_t)B.nblk * 4 + 64));
     u32 *seglen = ctx->d_dec2.as<u32>();
     u32 *segnext = seglen + (size_t)B.nblk * sstride;
@@ -244,6 +250,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     *out_len = 0;
     BZ_CHECK(ctx->d_in.ensure(n + 64));
     BZ_CHECK(cudaMemcpyAsync(ctx->d_in.p, in, n, cudaMemcpyHostToDevice, st));
+    BZ_CHECK(cudaMemsetAsync(ctx->d_in.as<u8>() + n, 0, 64, st));       // word loads of the entropy stage read past the last byte
     // ---- 1. every bit offset that looks like a block or footer magic ----
     u32 cap = (u32)std::min<size_t>(n / 32 + 64, 0x7fffff00u);
     BZ_CHECK(ctx->d_dec1.ensure((size_t)cap * 8 + 64));
@@ -284,7 +291,7 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     BZ_CHECK(ctx->d_mtfstate.ensure((size_t)NB * ch_stride * 256));
     BZ_CHECK(ctx->d_chunkrec.ensure((size_t)NB * ch_stride * 8));
     BZ_CHECK(ctx->d_hdr.ensure((size_t)NB * sizeof(DecTables)));
-    BZ_CHECK(ctx->d_dec3.ensure((size_t)NB * (8 + 4 + 4 + 4 + 8 + 8 + 8) + 256));
+    BZ_CHECK(ctx->d_dec3.ensure((size_t)NB * (8 + 4 + 4 + 4 + 8 + 8 + 8 + 8) + 256));
     BZ_CHECK(ctx->d_crc.ensure((size_t)NB * 4));
     DecTables *d_tabs = ctx->d_hdr.as<DecTables>();
     u32 *d_gbit = ctx->d_gbits.as<u32>();
@@ -299,8 +306,9 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u32 *d_keys = d_len + NB;
     u32 *d_rand = d_keys + NB;
     u32 *d_se = d_rand + NB;
+    u64 *d_rend = (u64 *)(d_se + 2 * (size_t)NB);                // after the spans; 8-byte aligned (all counts are multiples of NB * 4, NB even)
     const u8 *d_bits = ctx->d_in.as<u8>();
-    if (!ctx->dec_attr_done) { BZ_CHECK(cudaFuncSetAttribute(k_dec_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BoundsSmem))); ctx->dec_attr_done = true; }
+    if (!ctx->dec_attr_done) { BZ_CHECK(cudaFuncSetAttribute(k_dec_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JRING_BYTES)); ctx->dec_attr_done = true; }
 
     auto read32 = [&](u64 bit) {                                // 32 bits at an arbitrary bit offset of the input
         size_t byte = (size_t)(bit >> 3); int sh = (int)(bit & 7);
@@ -312,7 +320,8 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     u64 expect = 32;                                            // bit offset where the next block / footer must start
     u32 combined = 0;                                           // running combined CRC of the current stream
     size_t total_out = 0;
-    std::vector<u64> starts;
+    std::vector<u64> starts, rends;
+    const u64 range_limit = [] { const char *e = getenv("BZ2B200_DEC_RANGE_LIMIT"); return e ? (u64)strtoull(e, nullptr, 10) : 0ull; }();
     std::vector<DecTail> db;
     std::vector<u32> hlen(NB), hkey(NB), hrand(NB), se(2 * (size_t)NB), crcs(NB);
     std::vector<u64> olen(NB), ooff(NB);
@@ -331,12 +340,55 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
             continue;
         }
         // ---- 2. entropy decode of the next candidate blocks (decode4.cuh) ----
-        starts.clear();
-        for (size_t k = ci; k < ncand && starts.size() < NB; k++) if (!(cand[k] & FOOT)) starts.push_back(cand[k]);
+        // A block's data cannot reach past the next candidate -- unless that one is a chance magic inside it: the walk
+        // then leaves the range its jump tables cover and finishes code by code.
+        starts.clear(); rends.clear();
+        u64 max_range = 0;
+        for (size_t k = ci; k < ncand && starts.size() < NB; k++) {
+            if (cand[k] & FOOT) continue;
+            u64 re = k + 1 < ncand ? (cand[k + 1] & ~FOOT) : (u64)n * 8;
+            if (range_limit) re = std::min(re, cand[k] + range_limit);     // test knob: as if a chance magic cut the range
+            starts.push_back(cand[k]); rends.push_back(re);
+            max_range = std::max(max_range, re - cand[k]);
+        }
         const u32 nb = (u32)starts.size();
         BZ_CHECK(cudaMemcpyAsync(d_starts, starts.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+        BZ_CHECK(cudaMemcpyAsync(d_rend, rends.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
         ctx->prof_begin(K_DEC_HEADER, 0); k_dec_header<<<nb, 32, 0, st>>>(d_bits, n, d_starts, ctx->d_sel.as<u8>(), sel_stride, d_tabs); LAUNCH_OK();
-        ctx->prof_begin(K_DEC_BOUNDS, n); k_dec_bounds<<<nb, 32, sizeof(BoundsSmem), st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, max_sym); LAUNCH_OK();
+        {   // group boundaries: jump tables (2 bytes per bit offset and table), and the walkers of the same blocks following
+            // them window by window from a second, high-priority stream (their few CTAs are placed as soon as the producer's
+            // first ones retire); in slices of the batch when the tables of all its blocks would not fit the budget
+            // (incompressible data: 88 MB per block).  The producer is launched first: a tool that serialises kernels in
+            // launch order (ncu, compute-sanitizer) then still terminates.
+            const u32 nwin_max = jump_windows(max_range);
+            const size_t jstride = (size_t)nwin_max * 6 * 2 * JW;
+            const size_t budget = (size_t)6 << 30;
+            const u32 slice = (u32)std::max<size_t>(1, std::min<size_t>(nb, budget / jstride));
+            BZ_CHECK(ctx->d_VALA.ensure((size_t)slice * jstride));
+            BZ_CHECK(ctx->d_VALB.ensure((size_t)slice * nwin_max * 4));
+            u32 *d_flags = ctx->d_VALB.as<u32>();
+            if (!ctx->s_hi) {
+                int lo = 0, hi = 0;
+                BZ_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                BZ_CHECK(cudaStreamCreateWithPriority(&ctx->s_hi, cudaStreamNonBlocking, hi));
+                for (int q = 0; q < 2; q++) BZ_CHECK(cudaEventCreateWithFlags(&ctx->ev_dec[q], cudaEventDisableTiming));
+            }
+            for (u32 b0 = 0; b0 < nb; b0 += slice) {
+                const u32 cnt = std::min(slice, nb - b0);
+                BZ_CHECK(cudaMemsetAsync(d_flags, 0, (size_t)cnt * nwin_max * 4, st));
+                BZ_CHECK(cudaEventRecord(ctx->ev_dec[0], st));                   // headers parsed, flags clear, the previous slice done
+                ctx->prof_begin(K_DEC_JUMPS, (u64)cnt * jstride);
+                k_dec_jumps<<<dim3(cnt, nwin_max), 256, 0, st>>>(d_bits, n, d_tabs, d_rend, ctx->d_VALA.as<u8>(), jstride, d_flags, nwin_max, b0); LAUNCH_OK();
+                BZ_CHECK(cudaStreamWaitEvent(ctx->s_hi, ctx->ev_dec[0], 0));
+                k_dec_bounds<<<cnt, 32, JRING_BYTES, ctx->s_hi>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_rend, ctx->d_VALA.as<u8>(), jstride, d_flags, nwin_max, d_gbit, max_sym, b0);
+                ctx->launches++;
+                if (cudaGetLastError() != cudaSuccess) { ctx->err = "decode: k_dec_bounds launch"; cudaStreamSynchronize(st); return BZ2B200_E_CUDA; }
+                BZ_CHECK(cudaEventRecord(ctx->ev_dec[1], ctx->s_hi));
+                ctx->prof_begin(K_DEC_BOUNDS, n);                                // as timed on the main stream: what the walk adds after the producer
+                BZ_CHECK(cudaStreamWaitEvent(st, ctx->ev_dec[1], 0));
+                ctx->prof_end(); ctx->launches--;
+            }
+        }
         dim3 gs((sel_stride + 127) / 128, nb);
         ctx->prof_begin(K_DEC_SYMS, n); k_dec_syms<<<gs, 128, 0, st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, d_sym, sym_stride); LAUNCH_OK();
         dim3 gch((ch_stride + 7) / 8, nb);

@@ -5,8 +5,8 @@
 // (Huffman decode and MTF replay symbol by symbol): 160 ms for 112 blocks, the GPU empty.  A bzip2 block has two
 // serial dependences -- where each Huffman code starts, and the MTF list -- and both are cut here:
 //   k_dec_header   one warp per block: symbol map, selectors, code lengths -> canonical tables + 10-bit LUTs
-//   k_dec_bounds   one lane per block walks the bit stream decoding only code LENGTHS (LUT probe, skip) and
-//                  records the bit offset of every 50-symbol group: the only sequential pass left
+//   k_dec_jumps / k_dec_bounds (decode_bounds.cuh)  the bit offset of every 50-symbol group: jump tables over all bit
+//                  offsets built in parallel, then one lane per block walks 7 look-ups per group
 //   k_dec_syms     one thread per group decodes its 50 symbols from that offset with the group's table
 //   k_dec_chunks<0> one warp per ~1024-symbol chunk (cut where no RUNA/RUNB run is open): bytes the chunk
 //                  produces, and the PERMUTATION its MTF ranks apply to the list (replayed on the identity)
@@ -59,37 +59,6 @@ struct BitBuf {
     __device__ u64 bitpos() const { return (u64)byte * 8 - (u64)nb; }
 };
 
-// Bit reader over 4-byte aligned words with the next word already in flight (the walk of k_dec_bounds is one
-// long dependent chain: a load issued when it is needed would add its latency to every sixth symbol).
-struct WordBits {
-    const u32 *w; u32 last, idx;             // idx = next word to fetch into `ahead`; last = index of the last word
-    u64 buf; int nb; u32 ahead;
-    __device__ __forceinline__ u32 fetch(u32 i) const { return __byte_perm(__ldg(w + min(i, last)), 0, 0x0123); }
-    __device__ void init(const u8 *in, size_t len, u64 bitpos) {     // `in` is 4-byte aligned, streams are < 4 GiB
-        w = (const u32 *)in; last = (u32)((len + 3) / 4) - 1u;
-        asm volatile("" : "+l"(w));          // keep the pointer in a register: ptxas otherwise re-reads the kernel
-                                             // parameter from the constant bank inside the walk (21% of its stalls)
-        u32 first = (u32)(bitpos >> 5);
-        buf = ((u64)fetch(first) << 32) | fetch(first + 1);
-        nb = 64;
-        idx = first + 3; ahead = fetch(first + 2);
-        int sk = (int)(bitpos & 31);
-        buf <<= sk; nb -= sk;
-    }
-    __device__ __forceinline__ void refill() {
-        if (nb <= 32) {
-            buf |= (u64)ahead << (32 - nb);
-            nb += 32;
-            ahead = fetch(idx);                                  // clamped: a corrupt stream cannot walk off the buffer
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(w + min(idx + 48u, last)));
-            idx++;
-        }
-    }
-    __device__ __forceinline__ u32 peek(int k) const { return (u32)(buf >> (64 - k)); }
-    __device__ __forceinline__ void skip(int k) { buf <<= k; nb -= k; }
-    __device__ u64 bitpos() const { return (u64)(idx - 1) * 32 - (u64)nb; }
-};
-
 // ---------------------------------------------------------------------------------------------------------
 // header: decompress.rs:98-260 + huf_decode_map (:426-486)
 // ---------------------------------------------------------------------------------------------------------
@@ -103,7 +72,8 @@ __global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const
     __shared__ u8 seq[256];
     __shared__ int s_T, s_alpha, s_status;
     __shared__ u32 s_G, s_crc, s_key, s_rand;
-    __shared__ u64 s_data;
+    __shared__ u64 s_data, s_selbit, s_lenbit;
+    __shared__ u32 s_perm[32];
     const int lane = threadIdx.x;
     u8 *sel = sel_all + (size_t)b * sel_stride;
     for (int i = lane; i < 256; i += 32) seq[i] = 0;
@@ -126,18 +96,84 @@ __global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const
         int T = (int)br.get(3);
         u32 G = br.get(15);
         if (!s_status && (T < 2 || T > 6 || G < 1 || G > sel_stride)) s_status = 3;
-        if (!s_status) {                                        // selectors: unary index into an MTF list (decompress.rs:140-203)
-            u8 l6[6] = {0, 1, 2, 3, 4, 5};
-            for (u32 g = 0; g < G && !s_status; g++) {
-                int j = 0;
-                while (br.get(1)) { j++; if (j >= T) { s_status = 4; break; } }
-                if (s_status) break;
-                u8 v = l6[j];
-                for (int k = j; k > 0; k--) l6[k] = l6[k - 1];
-                l6[0] = v;
-                sel[g] = v;
+        s_T = T; s_alpha = alpha; s_G = G; s_selbit = br.bitpos();
+    }
+    __syncwarp();
+    // ---- selectors (decompress.rs:140-203): G unary numbers (j ones, then a zero), each an index into a move-to-front
+    // list of the table numbers.  Selector g ends at the g-th zero bit, so the warp finds them 1024 bits at a time
+    // (zeros per word, one scan); the MTF list has 6 entries, so a lane replays its share of the numbers on the
+    // identity list, the 32 results are composed in order, and the lane replays its share again from its true list.
+    if (s_status == 0) {
+        const int T = s_T;
+        const u32 G = s_G;
+        const u32 *wsrc = (const u32 *)in;
+        const u64 lastw = (u64)((n + 3) / 4) - 1;
+        u32 found = 0, carry = 0;
+        bool bad = false;
+        for (u64 c0 = s_selbit; found < G; c0 += 1024) {
+            const u64 bp = c0 + 32u * (u32)lane;
+            const u64 wi = bp >> 5;
+            const u32 hi = __byte_perm(__ldg(wsrc + min(wi, lastw)), 0, 0x0123), lo = __byte_perm(__ldg(wsrc + min(wi + 1, lastw)), 0, 0x0123);
+            const u32 w = __funnelshift_l(lo, hi, (u32)(bp & 31));
+            u32 m = ~w;                                         // set bits: the zeros, MSB first
+            const u32 nz = __popc(m);
+            const u32 inc = warp_incl_sum(nz);
+            const u32 tr = m ? (u32)(__ffs(m) - 1) : 32u;       // ones at the end of this word
+            u32 ptr = __shfl_up_sync(0xffffffffu, tr, 1);
+            if (lane == 0) ptr = carry;
+            u32 gidx = found + inc - nz;
+            int lastpos = -1;
+            while (m && gidx < G) {
+                const int pos = __clz(m);
+                const u32 j = lastpos < 0 ? ptr + (u32)pos : (u32)(pos - lastpos - 1);
+                if (j >= (u32)T) bad = true;
+                sel[gidx] = (u8)j;
+                if (gidx == G - 1) s_lenbit = bp + (u64)pos + 1;
+                gidx++; lastpos = pos;
+                m &= ~(0x80000000u >> pos);
+            }
+            if (nz == 0 && gidx < G) bad = true;                // 32 ones in a row inside the selectors
+            carry = __shfl_sync(0xffffffffu, tr, 31);
+            found += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (__any_sync(0xffffffffu, bad)) { if (lane == 0) s_status = 4; }
+        __syncwarp();
+        if (s_status == 0) {
+            const u32 per = (G + 31) / 32;
+            const u32 g0 = min(G, (u32)lane * per), g1 = min(G, g0 + per);
+            u32 Lp = 0x543210u;                                 // nibble k = table number at list position k
+            for (u32 g = g0; g < g1; g++) {
+                const u32 j4 = 4u * sel[g];
+                const u32 v = (Lp >> j4) & 15u, low = Lp & ((1u << j4) - 1u);
+                Lp = (Lp & ~((16u << j4) - 1u)) | (low << 4) | v;
+            }
+            s_perm[lane] = Lp;
+            __syncwarp();
+            if (lane == 0) {                                    // start list of every lane: compose in order
+                u32 S = 0x543210u;
+                for (int k = 0; k < 32; k++) {
+                    const u32 F = s_perm[k];
+                    s_perm[k] = S;
+                    u32 N = 0;
+                    for (int q = 0; q < 6; q++) N |= ((S >> (4u * ((F >> (4 * q)) & 15u))) & 15u) << (4 * q);
+                    S = N;
+                }
+            }
+            __syncwarp();
+            Lp = s_perm[lane];
+            for (u32 g = g0; g < g1; g++) {
+                const u32 j4 = 4u * sel[g];
+                const u32 v = (Lp >> j4) & 15u, low = Lp & ((1u << j4) - 1u);
+                Lp = (Lp & ~((16u << j4) - 1u)) | (low << 4) | v;
+                sel[g] = (u8)v;
             }
         }
+    }
+    __syncwarp();
+    if (lane == 0 && s_status == 0) {
+        const int T = s_T, alpha = s_alpha;
+        BitBuf br;
+        br.init(in, n, s_lenbit);
         for (int t = 0; t < T && !s_status; t++) {             // code lengths (decompress.rs:216-260)
             int c = (int)br.get(5);
             for (int s = 0; s < alpha && !s_status; s++) {
@@ -149,7 +185,7 @@ __global__ void __launch_bounds__(32) k_dec_header(const u8 *in, size_t n, const
                 len[t][s] = (u8)c;
             }
         }
-        s_T = T; s_alpha = alpha; s_G = G; s_data = br.bitpos();
+        s_data = br.bitpos();
     }
     __syncwarp();
     const int T = s_T, alpha = s_alpha;
@@ -209,7 +245,7 @@ __device__ __forceinline__ void load_tables(SmemTables &s, const DecTables *g) {
     for (int i = threadIdx.x; i < 6 * 22; i += blockDim.x) { (&s.limit[0][0])[i] = (&g->limit[0][0])[i]; (&s.base[0][0])[i] = (&g->base[0][0])[i]; }
 }
 
-// one Huffman symbol with table t; returns the symbol, or -1 on a malformed code.  R = BitBuf or WordBits.
+// one Huffman symbol with table t; returns the symbol, or -1 on a malformed code.  R = BitBuf.
 template <class R>
 __device__ __forceinline__ int decode_one(R &br, const SmemTables &s, int t, int alpha) {
     br.refill();
@@ -223,115 +259,6 @@ __device__ __forceinline__ int decode_one(R &br, const SmemTables &s, int t, int
     if (pi < 0 || pi >= alpha) return -1;
     br.skip(l);
     return (int)s.perm[t][pi];
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// group boundaries: the one sequential walk (decompress.rs:293-358 without the symbol work)
-// ---------------------------------------------------------------------------------------------------------
-// The walk is one dependent chain per block (probe, shift, probe ...), ~150 cycles per symbol with a one-symbol
-// table.  A 12-bit window usually holds TWO codes, so the pair table below halves the chain.
-// entry: [4:0] bits to skip (both codes if two fit, else the first), [6:5] codes covered (1 or 2), [11:7] length of
-// the first code alone, bit 12 = "special" (a code longer than 12 bits, or EOB among the covered codes), bit 13 =
-// the first symbol is EOB, bit 14 = the second is.  The walk's common path is probe -> shift with no selects and
-// one never-taken branch (a lone warp pays ~5 cycles per dependent instruction and ~15 per taken branch).
-constexpr int PAIRBITS = 12;
-struct BoundsSmem {
-    u16 pair[6][1 << PAIRBITS];
-    u16 perm[6][258];
-    int limit[6][22], base[6][22];
-};
-
-// canonical decode of the code at the top of the left-aligned `win` (valid bits: `avail`); returns length or 0
-__device__ __forceinline__ int canon_len(const DecTables *g, int t, u32 win, int avail, int alpha, int &sym) {
-    for (int l = 1; l <= 20 && l <= avail; l++) {
-        int code = (int)(win >> (32 - l));
-        if (code <= g->limit[t][l]) {
-            int pi = code + g->base[t][l];
-            if (pi < 0 || pi >= alpha) return 0;
-            sym = g->perm[t][pi];
-            return l;
-        }
-    }
-    return 0;
-}
-
-__global__ void __launch_bounds__(32) k_dec_bounds(const u8 *in, size_t n, const u8 *sel_all, u32 sel_stride,
-                                                   DecTables *tabs, u32 *gbit_all, u32 max_sym) {
-    u32 b = blockIdx.x;
-    extern __shared__ __align__(16) unsigned char bounds_smem[];
-    BoundsSmem &st = *(BoundsSmem *)bounds_smem;
-    DecTables *tb = tabs + b;
-    if (tb->status) return;
-    const int alpha = (int)tb->alpha;
-    const int T = (int)tb->T;
-    for (int i = threadIdx.x; i < 6 * 258; i += 32) (&st.perm[0][0])[i] = (&tb->perm[0][0])[i];
-    for (int i = threadIdx.x; i < 6 * 22; i += 32) { (&st.limit[0][0])[i] = (&tb->limit[0][0])[i]; (&st.base[0][0])[i] = (&tb->base[0][0])[i]; }
-    for (int t = 0; t < T; t++) {
-        for (int v = threadIdx.x; v < (1 << PAIRBITS); v += 32) {
-            u32 win = (u32)v << (32 - PAIRBITS);
-            int s1 = 0, s2 = 0;
-            int l1 = canon_len(tb, t, win, PAIRBITS, alpha, s1);
-            u32 e = 0x1000u;
-            if (l1) {
-                e = (u32)l1 | (1u << 5) | ((u32)l1 << 7);
-                if (s1 == alpha - 1) e |= 0x3000u;
-                else if (l1 < PAIRBITS) {
-                    int l2 = canon_len(tb, t, win << l1, PAIRBITS - l1, alpha, s2);
-                    if (l2) { e = (u32)(l1 + l2) | (2u << 5) | ((u32)l1 << 7); if (s2 == alpha - 1) e |= 0x5000u; }
-                }
-            }
-            st.pair[t][v] = (u16)e;
-        }
-    }
-    __syncwarp();
-    if (threadIdx.x != 0) return;
-    const u8 *sel = sel_all + (size_t)b * sel_stride;
-    u32 *gbit = gbit_all + (size_t)b * sel_stride;
-    const u32 G = tb->G;
-    const u64 data_bit = tb->data_bit;
-    WordBits br;
-    br.init(in, n, data_bit);
-    u32 g = 0, nsym = 0, status = 0;
-    bool done = false;
-    while (!done) {
-        if (g >= G) { status = 6; break; }                      // ran out of selectors before EOB
-        const u16 *pt = st.pair[sel[g]];
-        const int t = sel[g];
-        gbit[g] = (u32)(br.bitpos() - data_bit);
-        g++;
-        int rem = 50;                                            // every decoded symbol decrements rem, nsym is settled per group
-        while (rem > 0 && !done) {
-            br.refill();
-            // probes run back to back while more than 32 bits are buffered: the refill (a dozen instructions) stays out
-            // of this loop -- as predicated code inside it, it was issued on every probe
-            do {
-                u32 e = pt[br.peek(PAIRBITS)];
-                if (__builtin_expect((e & 0x1000u) != 0 || rem < 2, 0)) {
-                    // rare: EOB in the window, a code longer than 12 bits, or the last symbol of the group
-                    u32 l1 = (e >> 7) & 31u;
-                    if (l1 == 0) {
-                        int l = PAIRBITS + 1;
-                        int code = (int)br.peek(l);
-                        while (l <= 20 && code > st.limit[t][l]) { l++; code = (int)br.peek(l); }
-                        int pi = l <= 20 ? code + st.base[t][l] : -1;
-                        if (pi < 0 || pi >= alpha) { status = 7; done = true; break; }
-                        br.skip(l);
-                        rem--;
-                        if ((int)st.perm[t][pi] == alpha - 1) { done = true; break; }
-                    } else if (e & 0x2000u) { br.skip((int)l1); rem--; done = true; break; }                  // the first symbol is EOB
-                    else if ((e & 0x4000u) && rem >= 2) { br.skip((int)(e & 31u)); rem -= 2; done = true; break; }   // the second one is
-                    else if (rem >= 2 && ((e >> 5) & 3u) == 2u) { br.skip((int)(e & 31u)); rem -= 2; }
-                    else { br.skip((int)l1); rem--; }            // one symbol (group end, or EOB belongs to the next group)
-                } else {
-                    br.skip((int)(e & 31u));
-                    rem -= (int)((e >> 5) & 3u);
-                }
-            } while (br.nb > 32 && rem > 0);
-        }
-        nsym += (u32)(50 - rem);
-        if (nsym > max_sym || br.bitpos() > (u64)n * 8 + 64) { status = 7; break; }
-    }
-    tb->status = status; tb->end_bit = br.bitpos(); tb->nsym = nsym; tb->ngroups = g;
 }
 
 // ---------------------------------------------------------------------------------------------------------

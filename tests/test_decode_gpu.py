@@ -116,3 +116,17 @@ def test_randomised_block(engine, ref):
     stream = bz.merge_streams(9, [(bytes(pb), len(pb) * 8 - pad, [crc])])
     assert bz2.decompress(stream) == data                          # libbz2 agrees that this IS the stream of `data`
     assert engine.decompress(stream) == data
+
+
+def test_walk_leaves_its_jump_tables(engine, monkeypatch):
+    """A chance block magic inside a block's data cuts the range the jump tables of k_dec_jumps cover (decode.cu); the
+    walk must then finish code by code with the same result.  BZ2B200_DEC_RANGE_LIMIT cuts every range artificially:
+    inside the first window, in the middle of a block, and at zero bits (no tables at all)."""
+    data = corpus.text(1_500_000, 33).tobytes() + bytes(np.random.default_rng(5).integers(0, 256, 200_000, dtype=np.uint8))
+    streams = [engine.compress(data, 9), bz2.compress(data, 3)]
+    for limit in ("1", "700", "100000", "1500001"):
+        monkeypatch.setenv("BZ2B200_DEC_RANGE_LIMIT", limit)
+        for s in streams:
+            assert engine.decompress(s) == data, limit
+    monkeypatch.delenv("BZ2B200_DEC_RANGE_LIMIT")
+    assert engine.decompress(streams[0]) == data
