@@ -151,31 +151,49 @@ __global__ void __launch_bounds__(256) k_mtf_scan(const u32 *len, const u32 *use
     int run = used ? -(int)(idx0 + 1) : -100000 - (int)s;
     const int *src = lp + (size_t)b * nch_stride * 256;
     int *dst = pm + (size_t)b * nch_stride * 256;
-#pragma unroll 4
+#pragma unroll 16
     for (u32 c = 0; c < nch; c++) {
         int v = src[(size_t)c * 256 + s];
         dst[(size_t)c * 256 + s] = run;
         if (v >= 0) run = v;
     }
-    if (threadIdx.x == 0) {
-        const ChunkAgg *g = agg + (size_t)b * nch_stride;
-        u32 zb = 0, sum = 0;
-        for (u32 c = 0; c < nch; c++) {
-            ChunkAgg x = g[c];
-            zbefore[(size_t)b * nch_stride + c] = zb;
-            ooff[(size_t)b * nch_stride + c] = sum;
-            if (x.flags & 1u) {
-                zb += x.lead;
-                if (x.flags & 2u) { sum += 31 - __clz(zb + 1); zb = 0; }
-            } else {
-                u32 z = zb + x.lead;
-                if (z) sum += 31 - __clz(z + 1);
-                sum += x.count_rest;
-                zb = x.trail;
+    // zero-run bookkeeping -> output offset and pending zeros of every chunk: a sequential pass, but over shared memory
+    // (as one thread reading global memory it paid a DRAM round trip per chunk: 0.1 ms however small the batch)
+    constexpr u32 TILE = 512;
+    __shared__ ChunkAgg sagg[TILE];
+    __shared__ u32 szb[TILE], ssum[TILE];
+    __shared__ u32 c_zb, c_sum;
+    if (threadIdx.x == 0) { c_zb = 0; c_sum = 0; }
+    const ChunkAgg *g = agg + (size_t)b * nch_stride;
+    for (u32 c0 = 0; c0 < nch; c0 += TILE) {
+        const u32 cn = min(TILE, nch - c0);
+        for (u32 i = threadIdx.x; i < cn; i += 256) sagg[i] = g[c0 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 zb = c_zb, sum = c_sum;
+            for (u32 i = 0; i < cn; i++) {
+                ChunkAgg x = sagg[i];
+                szb[i] = zb; ssum[i] = sum;
+                if (x.flags & 1u) {
+                    zb += x.lead;
+                    if (x.flags & 2u) { sum += 31 - __clz(zb + 1); zb = 0; }
+                } else {
+                    u32 z = zb + x.lead;
+                    if (z) sum += 31 - __clz(z + 1);
+                    sum += x.count_rest;
+                    zb = x.trail;
+                }
             }
+            c_zb = zb; c_sum = sum;
         }
-        m_out[b] = sum + 1;     // + EOB
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < cn; i += 256) {
+            zbefore[(size_t)b * nch_stride + c0 + i] = szb[i];
+            ooff[(size_t)b * nch_stride + c0 + i] = ssum[i];
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) m_out[b] = c_sum + 1;     // + EOB
 }
 
 #include "mtf_emit3.cuh"   // k_mtf_emit3: position-parallel replay, the version that is launched
