@@ -15,7 +15,10 @@
  *     overlap (pageable memory works, the copies then block).  _dev functions take DEVICE
  *     pointers on the context's GPU (used for HBM-resident measurement); device OUTPUT buffers
  *     (d_out, d_dst) and the d_src of bz2b200_shift_bits_dev must be 4-byte aligned (the bit
- *     merge works on 32-bit words): BZ2B200_E_ARG otherwise.
+ *     merge works on 32-bit words): BZ2B200_E_ARG otherwise.  A context works on its own
+ *     non-blocking CUDA streams and returns when its work is complete: whatever the caller
+ *     still has in flight on a device buffer it passes (a copy into d_in, a memset of d_out)
+ *     must have finished before the call.
  *   - a context owns one GPU (streams, workspaces).  Calls on one context are serialised
  *     by an internal mutex; use one context per GPU for multi-GPU sharding.
  *   - there is no CPU fallback: if no CUDA device is usable, bz2b200_create fails.

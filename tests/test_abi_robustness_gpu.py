@@ -82,6 +82,7 @@ def test_bad_arguments(engine):
     # device entry points: output pointers must be 4-byte aligned (the bit merge works on 32-bit words)
     d_in = torch.from_numpy(data).cuda()
     d_out = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     assert L.bz2b200_compress_stream_dev(engine._h, d_in.data_ptr(), data.size, 9, d_out.data_ptr() + 1, 1 << 19, C.byref(n)) == bz.E_ARG
     assert L.bz2b200_shift_bits_dev(engine._h, d_out.data_ptr() + 2, 100, 3, d_out.data_ptr() + 4096) == bz.E_ARG
     assert L.bz2b200_compress_stream_dev(engine._h, d_in.data_ptr(), data.size, 9, d_out.data_ptr(), 1 << 20, C.byref(n)) == bz.OK

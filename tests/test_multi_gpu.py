@@ -45,9 +45,10 @@ def test_worlds_produce_the_single_gpu_stream(engine, data80, world):
 
 def test_several_windows_per_rank(engine, data80, monkeypatch):
     """A rank works through its windows one after the other while the next window's upload and the previous window's
-    download are in flight (two buffers each): 3 and 5 windows per rank must give the same bytes."""
+    download are in flight (two buffers each): 3 and 5 windows per rank must give the same bytes, and so must two windows
+    of unequal size (the first one is the smaller: BZ2B200_MULTI_FIRST_PCT)."""
     want = engine.compress(data80, 9)
-    for per, world in ((3, 2), (5, 3)):
+    for per, world in ((3, 2), (5, 3), (2, 2), (2, 4)):
         monkeypatch.setenv("BZ2B200_MULTI_WINDOWS", str(per))
         m = bz.MultiEngine(_devices(world))
         try:

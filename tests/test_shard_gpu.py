@@ -28,6 +28,7 @@ def _sharded(engine, data, level, world, window_slack):
         while True:
             win_len = min(total - lo, hi - lo + slack)
             d_win = d_in[lo:lo + win_len].clone()
+            torch.cuda.synchronize()        # the context works on its own non-blocking stream: torch's copy must have landed
             if r % 2 == 0:
                 engine.shard_scan(d_win.data_ptr(), lo, win_len, total, level)     # optional early phase
             try:
@@ -38,6 +39,7 @@ def _sharded(engine, data, level, world, window_slack):
                 assert lo + win_len < total
                 slack *= 4
         d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         bits, crcs = engine.shard_compress(nb, d_out.data_ptr(), cap)
         parts.append((d_out, bits, crcs))
         assert nxt >= min(hi, total)
@@ -51,6 +53,7 @@ def _sharded(engine, data, level, world, window_slack):
     for d_out, bits, crcs in parts:
         phase = pos % 8
         d_shift = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         engine.shift_bits(d_out.data_ptr(), bits, phase, d_shift.data_ptr())
         nby = (bits + phase + 7) // 8
         final[pos // 8:pos // 8 + nby].bitwise_or_(d_shift[:nby])
