@@ -329,10 +329,10 @@ int bz2b200_compress_stream_multi(bz2b200_mctx *m, const uint8_t *in, size_t n, 
         size_t per_rank = (n + (size_t)m->n - 1) / (size_t)m->n;
         size_t per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (per_rank >= 2 * WMIN && m->n >= 4) ? 2 : 1);
         if (const char *e = getenv("BZ2B200_MULTI_WINDOWS")) { int v = atoi(e); if (v >= 1) per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (size_t)v); }
-        // The first window of every rank is the smaller one (30% of its share): all ranks upload at once and share the
+        // The first window of every rank is the smaller one (25% of its share): all ranks upload at once and share the
         // host's memory bandwidth, and nothing can be compressed before the first windows are on the devices (measured on
         // 8 GPUs: 8 x 50 MB arrive after 3.3 ms); the larger second windows arrive under the first ones' kernels.
-        size_t first_pct = 30;
+        size_t first_pct = 25;
         if (const char *e = getenv("BZ2B200_MULTI_FIRST_PCT")) { int v = atoi(e); if (v >= 5 && v <= 100) first_pct = (size_t)v; }
         std::vector<size_t> round_sz(per);
         for (size_t q = 0; q < per; q++) round_sz[q] = (per_rank + per - 1) / per;
