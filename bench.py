@@ -141,21 +141,27 @@ def bzip2_cli_rate(data, level):
 def ref_path_accounting(eng, data, level, limit=48):
     """#blocks native / sais-valid / sais-divergent.  The device counts the blocks the reference's selector
     (bwt_sort.rs:29) sends to SA-IS; here (outside any timed region) the oracle's bug-for-bug EXACT mode runs on exactly
-    those blocks (the first `limit` of them): where its BWT equals the true one the reference's bytes are ours
-    ("sais_valid"), where it differs the reference's block does not decode ("sais_divergent")."""
+    those blocks (the first `limit` of them): where its BWT and origin pointer equal the true ones the reference's bytes
+    are ours ("sais_valid"); where only the origin pointer differs the block is fully periodic and the reference names
+    another row of the same class of equal rotations -- a valid block, 24 bits different from ours
+    ("sais_valid_other_origin"); where the BWT differs the reference's block does not decode
+    ("sais_divergent")."""
     from oracle import pyref
     blocks = eng.rle1_split(data, level)
     flagged = [b for _, b, _, _ in blocks if len(b) > 5000 and pyref.lms_count(b) <= 1499]
-    valid = div = 0
+    valid = other = div = 0
     for b in flagged[:limit]:
         k1, w1, _ = pyref.bwt_encode(b, pyref.EXACT)
         k2, w2, _ = pyref.bwt_encode(b, pyref.SPEC_FAST)
         if (k1, w1) == (k2, w2):
             valid += 1
+        elif w1 == w2:
+            other += 1
         else:
             div += 1
     return {"blocks": len(blocks), "native": len(blocks) - len(flagged), "sais": len(flagged),
-            "sais_checked": min(limit, len(flagged)), "sais_valid": valid, "sais_divergent": div}
+            "sais_checked": min(limit, len(flagged)), "sais_valid": valid, "sais_valid_other_origin": other,
+            "sais_divergent": div}
 
 
 def workload_config(level, per, total, world):

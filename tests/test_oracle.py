@@ -153,3 +153,34 @@ def test_exact_mode_reports_sais_divergence(ref):
     assert st["n_blocks"] == 1 and st["n_sais"] + st["n_native"] == 1
     if st["n_sais_divergent"] == 0:
         assert bz2.decompress(out) == data
+
+
+def test_spec_equals_spec_fast_on_full_size_blocks(ref):
+    """The stream-level parity tests use SPEC_FAST (prefix doubling); the reference's native path is SPEC (comparison
+    sort of the rotations, bwt_sort.rs:39-43).  Three blocks of the level-9 maximum size, one per corpus family."""
+    n = 9 * 100000 - 19 + 5
+    for name, data in (("text", corpus.text(n, 11)), ("markov", corpus.markov(n, 12)), ("mixed", corpus.mixed(n, 13))):
+        blk = data.tobytes()
+        k1, b1, _ = ref.bwt_encode(blk, ref.SPEC)
+        k2, b2, _ = ref.bwt_encode(blk, ref.SPEC_FAST)
+        assert (k1, b1) == (k2, b2), name
+
+
+def test_periodic_block_on_the_sais_path_names_another_row(ref):
+    """a fully periodic block (x = u^k) that the reference's selector routes to SA-IS gets a valid BWT but
+    not the first row of rotation 0's class as its origin pointer: the suffix sort of the rotated string (sentinel
+    smallest) orders the k equal rotations by suffix length, shortest first, so the row is
+    first_row + (off - 1) // |u| with off = duval(x) (sais_fallback.rs:601, :781-804).  The engine (like SPEC) writes the
+    first row: the two streams decode to the same bytes and differ in the 24-bit origin pointer only; bench.py reports
+    such blocks as `sais_valid_other_origin`."""
+    for u in (b"aaab", b"aaaaaaab", b"abcd"):
+        x = u * (8000 // len(u))
+        assert ref.lms_count(x) <= 1499 and len(x) > 5000            # the selector sends it to SA-IS
+        ke, be, path = ref.bwt_encode(x, ref.EXACT)
+        ks, bs, _ = ref.bwt_encode(x, ref.SPEC)
+        assert path == 1 and be == bs
+        off = ref.duval(x)
+        assert off >= 1 and ke == ks + (off - 1) // len(u) and ke != ks
+        se, ss = ref.compress_stream(x, 9, ref.EXACT), ref.compress_stream(x, 9, ref.SPEC)
+        assert se != ss and bz2.decompress(se) == x and bz2.decompress(ss) == x
+        assert ref.bwt_decode(ke, be) == x and ref.bwt_decode(ks, bs) == x
