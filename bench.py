@@ -117,8 +117,11 @@ def cpu_reference_rate(data, level, sample_mb, threads):
         sample_mb = max(2, min(len(data) // (1 << 20), int(threads * 1.8)))     # ~2 blocks per thread
     sample = data[:sample_mb << 20].tobytes()
     t0 = time.perf_counter()
-    out = pyref.compress_stream(sample, level, pyref.SPEC, threads=threads)
+    out, st = pyref.compress_stream(sample, level, pyref.SPEC, threads=threads, want_stats=True)
     dt = time.perf_counter() - t0
+    # Huffman (weight, syms) ties between distinct nodes, and those at list lengths 21..49 where rustc 1.65's
+    # sort_unstable is not pinned by the reference's tests: 0 means the sample never enters that window
+    cpu_reference_rate.ties = {"tie_events": int(st["tie_events"]), "tie_events_unpinned": int(st["tie_unpinned"])}
     return len(sample) / 1e6 / dt, dt, len(sample), len(out)
 
 
@@ -509,7 +512,8 @@ def _main(args, real_stdout):
         "roofline": roof,
         "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "first %.0f MB of the same workload in %.1f s: C restatement of the reference "
-                                   "(native comparison-sort BWT), %d pthreads over blocks" % (cpu_bytes / 1e6, cpu_dt, threads)},
+                                   "(native comparison-sort BWT), %d pthreads over blocks" % (cpu_bytes / 1e6, cpu_dt, threads),
+                         "huffman_ties": getattr(cpu_reference_rate, "ties", None)},
         "device_ms_per_step": float(np.mean(dev_ms)),
         "stage_ms": stage,
         "top_kernels": [{"kernel": k, "ms": v[0] / args.steps, "launches": v[1] // args.steps,

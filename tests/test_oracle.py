@@ -184,3 +184,13 @@ def test_periodic_block_on_the_sais_path_names_another_row(ref):
         se, ss = ref.compress_stream(x, 9, ref.EXACT), ref.compress_stream(x, 9, ref.SPEC)
         assert se != ss and bz2.decompress(se) == x and bz2.decompress(ss) == x
         assert ref.bwt_decode(ke, be) == x and ref.bwt_decode(ks, bs) == x
+
+
+def test_huffman_ties_stay_out_of_the_unpinned_window(ref):
+    """equal (weight, syms) keys of distinct nodes are ordered by rustc 1.65's sort_unstable, which no test
+    of the reference pins for list lengths 21..49.  The oracle counts such events (`tie_unpinned`); samples of the
+    benchmark corpora must not contain any, otherwise their parity claim would rest on an unpinned rule."""
+    for name, data in (("text", corpus.text(3_000_000, 2)), ("markov", corpus.markov(2_000_000, 6)),
+                       ("mixed", corpus.mixed(2_000_000, 5))):
+        _, st = ref.compress_stream(data.tobytes(), 9, ref.SPEC_FAST, threads=4, want_stats=True)
+        assert st["tie_unpinned"] == 0, (name, st["tie_events"], st["tie_unpinned"])
