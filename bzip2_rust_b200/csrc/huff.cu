@@ -249,38 +249,56 @@ __global__ void __launch_bounds__(256) k_huf_gbits(const u16 *sym, const u32 *m_
     u32 cnt = min((u32)(256 * BZ_GROUP), m - first);
     for (u32 i = threadIdx.x; i < cnt; i += 256) ssym[i] = s[first + i];
     for (int i = threadIdx.x; i < NSYM; i += 256) stab[i] = W.tab64[(size_t)b * NSYM + i];
+    const u8 *sel = W.sel + (size_t)b * W.sel_stride;
+    __shared__ u8 ssel[256];
+    __shared__ int s_last[6];
+    const int T = (int)W.misc[b * 8 + 0];
+    ssel[threadIdx.x] = g0 + threadIdx.x < G ? sel[g0 + threadIdx.x] : (u8)0;
+    if (threadIdx.x < 6) s_last[threadIdx.x] = -1;
     __syncthreads();
-    int T = (int)W.misc[b * 8 + 0];
+    for (int hi = (int)g0; hi > 0; hi -= 256) {                  // last use of every table before g0 (all threads take part)
+        int j = hi - 1 - (int)threadIdx.x;
+        if (j >= 0) { int u = sel[j]; if (u < 6) atomicMax(&s_last[u], j); }
+        __syncthreads();
+        bool all = true;
+        for (int t = 0; t < T; t++) all = all && s_last[t] >= 0;
+        __syncthreads();
+        if (all) break;
+    }
     u32 g = g0 + threadIdx.x;
     if (g >= G) return;
-    const u8 *sel = W.sel + (size_t)b * W.sel_stride;
-    int v = sel[g];
+    int v = ssel[threadIdx.x];
     u32 a = threadIdx.x * BZ_GROUP, e = min(a + BZ_GROUP, cnt);
     u64 acc = 0;
     for (u32 i = a; i < e; i++) acc += stab[ssym[i]];
     W.gbits[(size_t)b * W.sel_stride + g] = (u32)((acc >> (10 * v)) & 1023);
-    // selector MTF position (huffman.rs:237-275) by look-back
-    // (16 selectors per load: a table that was last used thousands of groups ago, with fewer than T - 1 others in
-    // between, made this one dependent byte load per group looked at -- 0.26 ms whatever the batch size)
-    u32 mask = 0; int pos = -1;
-    for (int j = (int)g - 1; j >= 0 && pos < 0;) {
-        const int base = j & ~15;
-        const uint4 q = *(const uint4 *)(sel + base);           // sel_stride is a multiple of 256
-        const u32 w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 15; k >= 0; k--) {
-            if (k <= j - base && pos < 0) {
-                int u = (int)((w4[k >> 2] >> (8 * (k & 3))) & 255u);
-                if (u == v) pos = __popc(mask);
-                else {
-                    mask |= 1u << u;
-                    if (__popc(mask) == T - 1) pos = T - 1;
-                }
-            }
+    // selector MTF position (huffman.rs:237-275) = number of distinct tables used since the last use of v.  Looking back
+    // selector by selector is one dependent load per step, and a table that was last used thousands of groups ago (with
+    // fewer than T - 1 others in between) made one thread do that alone: 0.2-0.3 ms whatever the batch size.  So: the CTA
+    // first finds, together, the last use of every table before its 256 groups; a thread then looks back inside the CTA's
+    // groups (shared memory) and, if that does not decide, through those at most six positions.
+    int pos = -1;
+    {
+        u32 mask = 0;
+        for (int k = (int)threadIdx.x - 1; k >= 0; k--) {
+            int u = ssel[k];
+            if (u == v) { pos = __popc(mask); break; }
+            mask |= 1u << u;
+            if (__popc(mask) == T - 1) { pos = T - 1; break; }
         }
-        j = base - 1;
+        if (pos < 0) {
+            u32 visited = 0;
+            for (int it = 0; it < T && pos < 0; it++) {
+                int best = -1, bt = -1;
+                for (int t = 0; t < T; t++) if (!((visited >> t) & 1u) && s_last[t] > best) { best = s_last[t]; bt = t; }
+                if (bt < 0) break;
+                visited |= 1u << bt;
+                if (bt == v) pos = __popc(mask);
+                else if (!((mask >> bt) & 1u)) { mask |= 1u << bt; if (__popc(mask) == T - 1) pos = T - 1; }
+            }
+            if (pos < 0) pos = __popc(mask) + __popc(~mask & ((1u << v) - 1));   // never used before: initial order 0..5
+        }
     }
-    if (pos < 0) pos = __popc(mask) + __popc(~mask & ((1u << v) - 1));   // never used before: initial order 0..5
     W.sbits[(size_t)b * W.sel_stride + g] = (u32)pos + 1;
 }
 
