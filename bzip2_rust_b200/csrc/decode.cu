@@ -12,9 +12,9 @@
 //                     from composing per-chunk permutations
 //   inverse BWT       stable counting sort of rows by byte = one pass of the BWT stage's radix kernels
 //                     (P[j] = row of the j-th smallest byte), then the n-step pointer chase of
-//                     bwt_decode is cut into ~n/256 segments at splitter rows: k_ibwt_chase measures
-//                     every segment in parallel, k_ibwt_rank orders them from the origin pointer,
-//                     k_ibwt_write replays each segment at its output offset
+//                     bwt_decode is cut into ~n/32 segments at splitter rows: k_ibwt_chase measures
+//                     every segment in parallel, a two-level walk orders them from the origin pointer
+//                     (k_ibwt_coarse / _crank / _fill), k_ibwt_write replays each segment at its output offset
 //   k_dec_rle1_*      inverse RLE1 (count pass, then write pass at the block's output offset)
 //   CRC               block CRCs with the encoder's CRC kernels; combined CRC on the host.
 // The standard run semantics are used (a count byte follows every 4 equal bytes); the reference's
@@ -34,7 +34,7 @@ namespace {
 constexpr u64 MAGIC_BLOCK = 0x314159265359ull;
 constexpr u64 MAGIC_END = 0x177245385090ull;
 #ifndef BZ_IBWT_SPLIT
-#define BZ_IBWT_SPLIT 64
+#define BZ_IBWT_SPLIT 32
 #endif
 constexpr int SPLIT = BZ_IBWT_SPLIT;     // inverse BWT: one splitter row every SPLIT rows
 
@@ -82,11 +82,97 @@ __global__ void __launch_bounds__(256) k_ibwt_chase(const u32 *P, const u32 *len
     segnext[(size_t)b * sstride + j] = split_index(row, key, nreg);
 }
 
-// one thread per block: visit splitters in text order starting at the origin pointer until n rows are covered
-__global__ void __launch_bounds__(32) k_ibwt_rank(const u32 *len, const u32 *keys, const u32 *seglen, const u32 *segnext,
-                                                  u32 sstride, u32 *visit_split, u32 *visit_off, u32 vstride, u32 *nvisit) {
+// Ranking the splitters (which one is visited when, at which text offset) is a walk along segnext from the origin
+// pointer: serial, one dependent load per splitter.  Two levels keep it short: every CSPLIT-th splitter (and the origin's)
+// is a COARSE splitter; a thread per coarse splitter measures its stretch of the list (k_ibwt_coarse), one thread per
+// block walks the coarse list (k_ibwt_crank, ~n / (SPLIT * CSPLIT) steps), a thread per coarse visit then numbers the
+// splitters of its stretch (k_ibwt_fill).  A block whose permutation has several cycles (a periodic block walks its short
+// cycle many times; corrupt data) can visit more coarse splitters than exist: it is flagged and ranked by the plain walk.
+constexpr int CSPLIT = 64;
+struct CoarseGeom {                      // jk = the origin's splitter: regular (key on a splitter row) or the extra slot nreg
+    u32 nreg, ncr, jk; bool origin_regular_coarse;
+    __device__ CoarseGeom(u32 n, u32 key) {
+        nreg = (n + SPLIT - 1) / SPLIT;
+        ncr = (nreg + CSPLIT - 1) / CSPLIT;                       // regular coarse splitters; coarse index ncr = the origin's
+        jk = (key % SPLIT) == 0 ? key / SPLIT : nreg;
+        origin_regular_coarse = jk != nreg && (jk % CSPLIT) == 0;
+    }
+    __device__ bool is_coarse(u32 j) const { return ((j % CSPLIT) == 0 && j != nreg) || j == jk; }
+    __device__ u32 coarse_index(u32 j) const { return (j == jk && !origin_regular_coarse) ? ncr : j / CSPLIT; }
+    __device__ u32 splitter_of(u32 c) const { return c < ncr ? c * CSPLIT : jk; }
+    __device__ u32 origin_coarse() const { return origin_regular_coarse ? jk / CSPLIT : ncr; }
+};
+
+__global__ void __launch_bounds__(128) k_ibwt_coarse(const u32 *len, const u32 *keys, const u32 *seglen, const u32 *segnext,
+                                                     u32 sstride, u32 *clen, u32 *chops, u32 *cnext, u32 cstride) {
+    u32 b = blockIdx.y;
+    const CoarseGeom g(len[b], keys[b]);
+    u32 c = blockIdx.x * 128 + threadIdx.x;
+    if (c > g.ncr) return;
+    if (c == g.ncr && g.origin_regular_coarse) { clen[(size_t)b * cstride + c] = 0; chops[(size_t)b * cstride + c] = 0; cnext[(size_t)b * cstride + c] = 0; return; }
+    u32 j = g.splitter_of(c);
+    const u32 *sl = seglen + (size_t)b * sstride, *sn = segnext + (size_t)b * sstride;
+    u32 rows = 0, hops = 0;
+    do { rows += sl[j]; j = sn[j]; hops++; } while (!g.is_coarse(j) && hops <= g.nreg + 1);
+    clen[(size_t)b * cstride + c] = rows;
+    chops[(size_t)b * cstride + c] = hops;
+    cnext[(size_t)b * cstride + c] = g.coarse_index(j);
+}
+
+// one thread per block: coarse visits in text order; flag[b] = 1 when the bound is exceeded (several cycles)
+__global__ void __launch_bounds__(32) k_ibwt_crank(const u32 *len, const u32 *keys, const u32 *clen, const u32 *chops,
+                                                   const u32 *cnext, u32 cstride, u32 *cv_split, u32 *cv_off, u32 *cv_vbase,
+                                                   u32 *ncvisit, u32 *nvisit, u32 *flag, u32 vstride) {
     u32 b = blockIdx.x;
     if (threadIdx.x != 0) return;
+    u32 n = len[b];
+    const CoarseGeom g(n, keys[b]);
+    u32 c = g.origin_coarse();
+    u32 off = 0, v = 0, u = 0;
+    bool over = false;
+    while (off < n) {
+        if (u >= cstride) { over = true; break; }
+        cv_split[(size_t)b * cstride + u] = c;
+        cv_off[(size_t)b * cstride + u] = off;
+        cv_vbase[(size_t)b * cstride + u] = v;
+        off += clen[(size_t)b * cstride + c];
+        v += chops[(size_t)b * cstride + c];
+        c = cnext[(size_t)b * cstride + c];
+        u++;
+    }
+    if (v > vstride) over = true;
+    flag[b] = over ? 1u : 0u;
+    ncvisit[b] = over ? 0u : u;
+    if (!over) nvisit[b] = v;       // an upper bound: the last stretch may reach n before its last splitter (k_ibwt_write checks off < n)
+}
+
+// thread per coarse visit: the splitters of its stretch, in order
+__global__ void __launch_bounds__(128) k_ibwt_fill(const u32 *len, const u32 *keys, const u32 *seglen, const u32 *segnext,
+                                                   u32 sstride, const u32 *chops, const u32 *cv_split, const u32 *cv_off,
+                                                   const u32 *cv_vbase, const u32 *ncvisit, u32 cstride, u32 *visit_split,
+                                                   u32 *visit_off, u32 vstride) {
+    u32 b = blockIdx.y;
+    u32 u = blockIdx.x * 128 + threadIdx.x;
+    if (u >= ncvisit[b]) return;
+    const CoarseGeom g(len[b], keys[b]);
+    u32 c = cv_split[(size_t)b * cstride + u];
+    u32 j = g.splitter_of(c);
+    u32 off = cv_off[(size_t)b * cstride + u], v = cv_vbase[(size_t)b * cstride + u];
+    u32 hops = chops[(size_t)b * cstride + c];
+    const u32 *sl = seglen + (size_t)b * sstride, *sn = segnext + (size_t)b * sstride;
+    for (u32 i = 0; i < hops && v < vstride; i++) {
+        visit_split[(size_t)b * vstride + v] = j;
+        visit_off[(size_t)b * vstride + v] = off;
+        off += sl[j]; j = sn[j]; v++;
+    }
+}
+
+// one thread per FLAGGED block: visit splitters in text order starting at the origin pointer until n rows are covered
+__global__ void __launch_bounds__(32) k_ibwt_rank(const u32 *len, const u32 *keys, const u32 *seglen, const u32 *segnext,
+                                                  u32 sstride, u32 *visit_split, u32 *visit_off, u32 vstride, u32 *nvisit,
+                                                  const u32 *flag) {
+    u32 b = blockIdx.x;
+    if (threadIdx.x != 0 || !flag[b]) return;
     u32 n = len[b], key = keys[b];
     u32 nreg = (n + SPLIT - 1) / SPLIT;
     u32 j = (key % SPLIT) == 0 ? key / SPLIT : nreg;
@@ -162,7 +248,24 @@ static int ibwt_batch(bz2b200_ctx *ctx, const Batch &B, const u32 *d_keys, u8 *d
     ctx->prof_begin(K_RADIX_SCATTER0, B.total_n * 9); radix::k_radix_scatter<<<gr, BZ_THREADS, 0, st>>>(a); LAUNCH_OK();
     dim3 gs((B.max_n / SPLIT + 2 + 255) / 256, B.nblk);
     ctx->prof_begin(K_IBWT_CHASE, B.total_n * 4); k_ibwt_chase<<<gs, 256, 0, st>>>(P, B.len, d_keys, B.stride, seglen, segnext, sstride); LAUNCH_OK();
-    ctx->prof_begin(K_IBWT_RANK, 0); k_ibwt_rank<<<B.nblk, 32, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, vsplit, voff, vstride, nvisit); LAUNCH_OK();
+    {
+        u32 cstride = sstride / CSPLIT + 8;
+        BZ_CHECK(ctx->d_KEYA.ensure((size_t)B.nblk * cstride * 4 * 6 + (size_t)B.nblk * 8 + 64));
+        u32 *clen = ctx->d_KEYA.as<u32>();
+        u32 *chops = clen + (size_t)B.nblk * cstride, *cnext = chops + (size_t)B.nblk * cstride;
+        u32 *cv_split = cnext + (size_t)B.nblk * cstride, *cv_off = cv_split + (size_t)B.nblk * cstride;
+        u32 *cv_vbase = cv_off + (size_t)B.nblk * cstride;
+        u32 *ncvisit = cv_vbase + (size_t)B.nblk * cstride, *flag = ncvisit + B.nblk;
+        dim3 gc((cstride + 127) / 128, B.nblk);
+        ctx->prof_begin(K_IBWT_RANK, 0);
+        k_ibwt_coarse<<<gc, 128, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, clen, chops, cnext, cstride); LAUNCH_OK();
+        ctx->prof_begin(K_IBWT_RANK, 0);
+        k_ibwt_crank<<<B.nblk, 32, 0, st>>>(B.len, d_keys, clen, chops, cnext, cstride, cv_split, cv_off, cv_vbase, ncvisit, nvisit, flag, vstride); LAUNCH_OK();
+        ctx->prof_begin(K_IBWT_RANK, 0);
+        k_ibwt_fill<<<gc, 128, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, chops, cv_split, cv_off, cv_vbase, ncvisit, cstride, vsplit, voff, vstride); LAUNCH_OK();
+        ctx->prof_begin(K_IBWT_RANK, 0);
+        k_ibwt_rank<<<B.nblk, 32, 0, st>>>(B.len, d_keys, seglen, segnext, sstride, vsplit, voff, vstride, nvisit, flag); LAUNCH_OK();
+    }
     dim3 gv((vstride + 255) / 256, B.nblk);
     ctx->prof_begin(K_IBWT_WRITE, B.total_n * 6); k_ibwt_write<<<gv, 256, 0, st>>>(P, B.T, B.len, d_keys, B.stride, vsplit, voff, vstride, nvisit, d_out); LAUNCH_OK();
     return BZ2B200_OK;
