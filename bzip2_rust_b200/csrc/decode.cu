@@ -399,6 +399,8 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
     DecTables *d_tabs = ctx->d_hdr.as<DecTables>();
     u32 *d_gbit = ctx->d_gbits.as<u32>();
     u16 *d_sym = ctx->d_sym.as<u16>();
+    BZ_CHECK(ctx->d_KEYB.ensure((size_t)NB * sym_stride));
+    u8 *d_vid = ctx->d_KEYB.as<u8>();                           // start-list position selected by every MTF symbol (k_dec_chunks -> k_dec_expand)
     u8 *d_lists = ctx->d_mtfstate.as<u8>();
     u32 *d_ccount = ctx->d_chunkrec.as<u32>();
     u32 *d_coff = d_ccount + (size_t)NB * ch_stride;
@@ -495,9 +497,9 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
         dim3 gs((sel_stride + 127) / 128, nb);
         ctx->prof_begin(K_DEC_SYMS, n); k_dec_syms<<<gs, 128, 0, st>>>(d_bits, n, ctx->d_sel.as<u8>(), sel_stride, d_tabs, d_gbit, d_sym, sym_stride); LAUNCH_OK();
         dim3 gch((ch_stride + 7) / 8, nb);
-        ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<0><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
+        ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, ch_stride, d_vid, max_block); LAUNCH_OK();
         ctx->prof_begin(K_DEC_CHUNK_SCAN, 0); k_dec_chunk_scan<<<nb, 256, 0, st>>>(d_tabs, d_lists, d_ccount, d_coff, ch_stride, max_block); LAUNCH_OK();
-        ctx->prof_begin(K_DEC_CHUNKS, 0); k_dec_chunks<1><<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_ccount, d_coff, ch_stride, ctx->d_T.as<u8>(), stride, max_block); LAUNCH_OK();
+        ctx->prof_begin(K_DEC_EXPAND, 0); k_dec_expand<<<gch, 256, 0, st>>>(d_tabs, d_sym, sym_stride, d_lists, d_coff, ch_stride, d_vid, ctx->d_T.as<u8>(), stride); LAUNCH_OK();
         db.resize(nb);
         BZ_CHECK(cudaMemcpy2DAsync(db.data(), sizeof(DecTail), (const u8 *)d_tabs + offsetof(DecTables, T), sizeof(DecTables),
                                    sizeof(DecTail), nb, cudaMemcpyDeviceToHost, st));

@@ -8,11 +8,13 @@
 //   k_dec_jumps / k_dec_bounds (decode_bounds.cuh)  the bit offset of every 50-symbol group: jump tables over all bit
 //                  offsets built in parallel, then one lane per block walks 7 look-ups per group
 //   k_dec_syms     one thread per group decodes its 50 symbols from that offset with the group's table
-//   k_dec_chunks<0> one warp per ~1024-symbol chunk (cut where no RUNA/RUNB run is open): bytes the chunk
-//                  produces, and the PERMUTATION its MTF ranks apply to the list (replayed on the identity)
+//   k_dec_chunks   one warp per ~1024-symbol chunk (cut where no RUNA/RUNB run is open): bytes the chunk
+//                  produces, the PERMUTATION its MTF ranks apply to the list (replayed on the identity), and
+//                  for every MTF symbol the start-list position of the value it selects
 //   k_dec_chunk_scan one CTA per block: composes the permutations in order -> the MTF list at every chunk
 //                  start, and the output offset of every chunk
-//   k_dec_chunks<1> the same walk with the real list: inverse MTF + RUNA/RUNB expansion -> the BWT string
+//   k_dec_expand   position parallel: start list [selected position] per MTF symbol, RUNA/RUNB expansion by a warp
+//                  scan -> the BWT string
 
 constexpr int LUTBITS = 10;
 constexpr int DCH = 1024;              // nominal symbols per MTF chunk
@@ -302,14 +304,12 @@ __device__ __forceinline__ u32 chunk_cut(const u16 *sym, u32 nsym, u32 c, u32 nc
     return i;
 }
 
-__device__ __forceinline__ bool below_start(u32 pos, u32 start) { return pos < start; }   // start is 0 in count mode
-
-// WRITE = 0: permutation of the chunk (perm_out[i] = start-list position of the value that ends at position i)
-//            and the number of bytes it produces.  WRITE = 1: decode with the real start list into tt.
-template <int WRITE>
+// Pass 1, one warp per chunk: the chunk's ranks replayed on the IDENTITY list.  Results: the permutation the chunk
+// applies (perm_out[i] = start-list position of the value that ends at position i), the number of bytes it produces,
+// and for every MTF symbol the start-list position of the value it selects (vid).  Once the start list of the chunk
+// is known (k_dec_chunk_scan) its bytes are slist[vid]: pass 2 (k_dec_expand) is position parallel.
 __global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const u16 *sym_all, u32 sym_stride,
-                                                    u8 *lists, u32 *ccount, const u32 *coff, u32 ch_stride,
-                                                    u8 *tt_all, u32 stride, u32 max_block) {
+                                                    u8 *lists, u32 *ccount, u32 ch_stride, u8 *vid_all, u32 max_block) {
     const u32 b = blockIdx.y;
     const DecTables *tb = tabs + b;
     if (tb->status) return;
@@ -319,54 +319,29 @@ __global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const
     const u32 c = blockIdx.x * 8 + w;
     if (c >= nch) return;
     const u16 *sym = sym_all + (size_t)b * sym_stride;
+    u8 *vid = vid_all + (size_t)b * sym_stride;
     const u32 eob = tb->alpha - 1;
     u32 i = chunk_cut(sym, nsym, c, nch);
     const u32 e = chunk_cut(sym, nsym, c + 1, nch);
     u8 *lst = lists + ((size_t)b * ch_stride + c) * 256;
     // MTF list across the warp: positions 0..31 one per lane, 32..255 as 7 bytes per lane (low 56 bits)
-    u32 fw; u64 tl = 0;
-    if (WRITE) {
-        fw = lst[lane];
+    u32 fw = (u32)lane; u64 tl = 0;
 #pragma unroll
-        for (int k = 0; k < 7; k++) tl |= (u64)lst[32 + 7 * lane + k] << (8 * k);
-    } else {
-        fw = (u32)lane;
-#pragma unroll
-        for (int k = 0; k < 7; k++) tl |= (u64)(32 + 7 * lane + k) << (8 * k);
-    }
+    for (int k = 0; k < 7; k++) tl |= (u64)(32 + 7 * lane + k) << (8 * k);
     const u64 LOW7 = 0x00FFFFFFFFFFFFFFull;
-    u8 *tt = tt_all + (size_t)b * stride;
-    const u32 o_start = WRITE ? coff[(size_t)b * ch_stride + c] : 0u;
-    u32 nblk = o_start;                       // output position (WRITE) / produced bytes (count)
+    u32 nblk = 0;                             // produced bytes
     u32 runlen = 0, runbit = 1;
-    u32 stage = 0;                            // byte staged by lane (nblk & 31)
     bool bad = false;
-    // a pending run repeats the list front: finish the partially staged 32-byte line, whole lines, stage the rest
-#define FLUSH_RUN()                                                                                     \
-    do {                                                                                                \
-        if (WRITE) {                                                                                    \
-            u32 cv = __shfl_sync(0xffffffffu, fw, 0);                                                   \
-            u32 head = min(runlen, (32u - (nblk & 31u)) & 31u);                                         \
-            if (head) {                                                                                 \
-                u32 slot = nblk & 31u;                                                                  \
-                if ((u32)lane >= slot && (u32)lane < slot + head) stage = cv;                           \
-                nblk += head; runlen -= head;                                                           \
-                if ((nblk & 31u) == 0 && !below_start(nblk - 32 + lane, o_start)) tt[nblk - 32 + lane] = (u8)stage; \
-            }                                                                                           \
-            while (runlen >= 32) { tt[nblk + lane] = (u8)cv; nblk += 32; runlen -= 32; }                \
-            if (runlen) { if ((u32)lane < runlen) stage = cv; nblk += runlen; }                         \
-        } else nblk += runlen;                                                                          \
-        runlen = 0;                                                                                     \
-    } while (0)
     for (u32 i0 = i; i0 < e && !bad; i0 += 32) {
         const int cnt = (int)min(32u, e - i0);
         const u32 mine = lane < cnt ? (u32)sym[i0 + lane] : 0u;
+        u32 myvid = 0;
         for (int q = 0; q < cnt; q++) {
             const u32 s = __shfl_sync(0xffffffffu, mine, q);
             if (s <= 1) { runlen += runbit << s; runbit <<= 1; if (runlen > max_block) { bad = true; break; } continue; }
             if (runlen) {
-                if (nblk - o_start + runlen > max_block) { bad = true; break; }
-                FLUSH_RUN();
+                if (nblk + runlen > max_block) { bad = true; break; }
+                nblk += runlen; runlen = 0;
             }
             runbit = 1;
             if (s == eob) break;
@@ -392,27 +367,91 @@ __global__ void __launch_bounds__(256) k_dec_chunks(const DecTables *tabs, const
                 }
                 fw = lane ? up : v;
             }
-            if (WRITE) {
-                if ((nblk & 31u) == (u32)lane) stage = v;
-                nblk++;
-                if ((nblk & 31u) == 0 && !below_start(nblk - 32 + lane, o_start)) tt[nblk - 32 + lane] = (u8)stage;
-            } else nblk++;
-            if (nblk - o_start > max_block) { bad = true; break; }
+            if (lane == q) myvid = v;
+            nblk++;
+            if (nblk > max_block) { bad = true; break; }
         }
+        if (lane < cnt) vid[i0 + lane] = (u8)myvid;
     }
     if (runlen && !bad) {                     // the run that ends exactly at the cut
-        if (nblk - o_start + runlen > max_block) bad = true;
-        else FLUSH_RUN();
+        if (nblk + runlen > max_block) bad = true;
+        else nblk += runlen;
     }
-#undef FLUSH_RUN
-    if (WRITE) {
-        u32 lb = nblk & ~31u;
-        if ((nblk & 31u) && (u32)lane < (nblk & 31u) && !below_start(lb + lane, o_start)) tt[lb + lane] = (u8)stage;
-    } else {
-        lst[lane] = (u8)fw;
+    lst[lane] = (u8)fw;
 #pragma unroll
-        for (int k = 0; k < 7; k++) lst[32 + 7 * lane + k] = (u8)(tl >> (8 * k));
-        if (lane == 0) ccount[(size_t)b * ch_stride + c] = bad ? 0xFFFFFFFFu : nblk;
+    for (int k = 0; k < 7; k++) lst[32 + 7 * lane + k] = (u8)(tl >> (8 * k));
+    if (lane == 0) ccount[(size_t)b * ch_stride + c] = bad ? 0xFFFFFFFFu : nblk;
+}
+
+// Pass 2, one warp per chunk, 32 symbols per step: an MTF symbol yields the byte slist[vid]; a RUNA/RUNB symbol that is
+// the k-th of its run yields (s + 1) << k copies of the list front, i.e. of the byte of the last MTF symbol before the
+// run (rle2_mtf.rs:223-262) -- counts and sources are lane-local, the output offsets one warp scan.
+__global__ void __launch_bounds__(256) k_dec_expand(const DecTables *tabs, const u16 *sym_all, u32 sym_stride,
+                                                    const u8 *lists, const u32 *coff, u32 ch_stride, const u8 *vid_all,
+                                                    u8 *tt_all, u32 stride) {
+    const u32 b = blockIdx.y;
+    const DecTables *tb = tabs + b;
+    if (tb->status) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 nsym = tb->nsym;
+    const u32 nch = (nsym + DCH - 1) / DCH;
+    const u32 c = blockIdx.x * 8 + w;
+    __shared__ u8 slist[8][256];
+    if (c >= nch) return;
+    const u16 *sym = sym_all + (size_t)b * sym_stride;
+    const u8 *vid = vid_all + (size_t)b * sym_stride;
+    const u32 eob = tb->alpha - 1;
+    const u32 i = chunk_cut(sym, nsym, c, nch);
+    const u32 e = chunk_cut(sym, nsym, c + 1, nch);
+    const u8 *lst = lists + ((size_t)b * ch_stride + c) * 256;
+    for (int k = lane; k < 256; k += 32) slist[w][k] = lst[k];
+    __syncwarp();
+    u8 *tt = tt_all + (size_t)b * stride;
+    u32 out = coff[(size_t)b * ch_stride + c];
+    u32 carry_k = 0;                          // run symbols at the end of the previous step (the run goes on)
+    u32 carry_front = 0;                      // start-list position of the list front at the start of the step
+    const u32 lt = (1u << lane) - 1u;
+    for (u32 i0 = i; i0 < e; i0 += 32) {
+        const bool valid = i0 + lane < e;
+        const u32 s = valid ? (u32)sym[i0 + lane] : 0xffffu;
+        const bool isrun = valid && s <= 1;
+        const bool ismtf = valid && s > 1 && s != eob;
+        const u32 myvid = ismtf ? (u32)vid[i0 + lane] : 0u;
+        const u32 mtfmask = __ballot_sync(0xffffffffu, ismtf);
+        const u32 below = mtfmask & lt;
+        const int src = below ? 31 - __clz(below) : -1;
+        u32 fv = __shfl_sync(0xffffffffu, myvid, src < 0 ? 0 : src);
+        if (src < 0) fv = carry_front;
+        u32 cntb = ismtf ? 1u : 0u;
+        if (isrun) {
+            const u32 k = src < 0 ? carry_k + (u32)lane : (u32)(lane - src - 1);
+            cntb = (s + 1u) << min(k, 24u);               // pass 1 bounded every run by the block size
+        }
+        u32 inc = cntb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        const u32 off = out + inc - cntb;
+        const u32 byte = slist[w][ismtf ? myvid : fv];
+        if (ismtf) tt[off] = (u8)byte;
+        else if (isrun && cntb <= 8) { for (u32 q = 0; q < cntb; q++) tt[off + q] = (u8)byte; }
+        u32 longmask = __ballot_sync(0xffffffffu, isrun && cntb > 8);
+        while (longmask) {                                 // long runs: the whole warp fills
+            const int L = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const u32 lo = __shfl_sync(0xffffffffu, off, L), ln = __shfl_sync(0xffffffffu, cntb, L);
+            const u32 bv = __shfl_sync(0xffffffffu, byte, L);
+            for (u32 q = lane; q < ln; q += 32) tt[lo + q] = (u8)bv;
+        }
+        out += __shfl_sync(0xffffffffu, inc, 31);
+        // state for the next step
+        if (mtfmask) {
+            const int last = 31 - __clz(mtfmask);
+            carry_front = __shfl_sync(0xffffffffu, myvid, last);
+            const u32 runmask = __ballot_sync(0xffffffffu, isrun);
+            carry_k = (u32)__popc(runmask & ~((2u << last) - 1u));      // run symbols after the last MTF symbol
+        } else {
+            carry_k += (u32)__popc(__ballot_sync(0xffffffffu, isrun));
+        }
     }
 }
 
