@@ -33,13 +33,25 @@ __global__ void __launch_bounds__(256) k_rle1_inv(const u8 *blk, const u32 *len,
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s_state = 0; s_off = 0; }
     __syncthreads();
-    constexpr int PT = 8;                                  // bytes per thread
+    constexpr int PT = 32;                                 // bytes per thread: the tile loop is a chain of CTA-wide scans,
+                                                           // 8 KB tiles keep it at ~110 steps per block (8: 440 steps, 2.4 -> 1.x ms)
     for (u32 base = 0; base < n; base += 256 * PT) {
         u32 i0 = base + threadIdx.x * PT;
         u8 c[PT + 1];
         c[0] = (i0 > 0 && i0 - 1 < n) ? r[i0 - 1] : 0;
+        if (i0 + PT <= n) {                                // blocks start 16-byte aligned (stride is a multiple of 4096)
+            const uint4 *q4 = (const uint4 *)(r + i0);
 #pragma unroll
-        for (int k = 0; k < PT; k++) c[k + 1] = (i0 + k < n) ? r[i0 + k] : 0;
+            for (int v = 0; v < PT / 16; v++) {
+                const uint4 q = q4[v];
+                const u32 wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[16 * v + k + 1] = (u8)(wv[k >> 2] >> (8 * (k & 3)));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PT; k++) c[k + 1] = (i0 + k < n) ? r[i0 + k] : 0;
+        }
         // thread function over its bytes
         u32 f = FN_ID;
 #pragma unroll
