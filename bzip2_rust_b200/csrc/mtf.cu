@@ -232,7 +232,8 @@ int bz_mtf_batch(bz2b200_ctx *ctx, const Batch &B, const u8 *d_bwt, u16 *d_sym, 
     ctx->prof_begin(K_MTF_SUMMARY, ne_act * 2); k_mtf_summary<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, lp, agg, B.stride, nch_stride); LAUNCH_OK();
     ctx->prof_begin(K_MTF_SCAN, ne_act * 2); k_mtf_scan<<<B.nblk, 256, 0, st>>>(B.len, usedbits, lp, pm, agg, zbefore, ooff, d_m, nch_stride); LAUNCH_OK();
     ctx->prof_begin(K_MTF_EMIT, ne_act * 3);
-    k_mtf_emit3<<<gch, BZ_THREADS, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
+    dim3 gem((maxch + EWPB - 1) / EWPB, B.nblk);
+    k_mtf_emit3<<<gem, 32 * EWPB, 0, st>>>(d_bwt, B.len, usedbits, pm, zbefore, ooff, d_m, d_sym, d_freq, B.stride, nch_stride);
     LAUNCH_OK();
     return BZ2B200_OK;
 }

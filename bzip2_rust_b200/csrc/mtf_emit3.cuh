@@ -38,10 +38,12 @@ __device__ __forceinline__ void mtf_emit_chunk(const u8 *L, u16 *so, u32 a, u32 
             myv[q] = slot < nused ? (u32)sused[slot] : 256u;
         }
     }
+    u32 chn = a + lane < e ? (u32)L[a + lane] : 0u;             // the next step's byte is loaded one step ahead
     for (u32 i0 = a; i0 < e; i0 += 32) {
         const int cntk = (int)min(32u, e - i0);
         const bool valid = lane < cntk;
-        const u32 ch = valid ? (u32)L[i0 + lane] : (0x100u | (u32)lane);
+        const u32 ch = valid ? chn : (0x100u | (u32)lane);
+        if (i0 + 32 + lane < e) chn = (u32)L[i0 + 32 + lane];
         u32 pb = __shfl_up_sync(0xffffffffu, ch, 1);
         if (lane == 0) pb = prev_last;
         const bool nz = valid && ch != pb;                  // rank != 0  <=>  differs from the previous byte
@@ -135,29 +137,36 @@ __device__ __forceinline__ void mtf_emit_chunk(const u8 *L, u16 *so, u32 a, u32 
 #ifndef BZ_MTF_COMPACT
 #define BZ_MTF_COMPACT 1
 #endif
-__global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit3(const u8 *Lall, const u32 *len, const u32 *usedbits,
+// EWPB warps (= chunks) per CTA: chunks differ in cost (distinct values per step), and a CTA keeps its slot until its
+// slowest warp is done -- with 8 warps 17% of the kernel's stall samples sat at the barrier in front of the freq flush.
+#ifndef BZ_MTF_EWPB
+#define BZ_MTF_EWPB 2
+#endif
+constexpr int EWPB = BZ_MTF_EWPB;
+__global__ void __launch_bounds__(32 * EWPB) k_mtf_emit3(const u8 *Lall, const u32 *len, const u32 *usedbits,
                                                           const int *pm, const u32 *zbefore, const u32 *ooff,
                                                           const u32 *m_in, u16 *sym, u32 *freq, u32 stride,
                                                           u32 nch_stride) {
     u32 b = blockIdx.y, n = len[b];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    u32 c = blockIdx.x * WPB + w;
+    u32 c = blockIdx.x * EWPB + w;
     u32 a = c * CH;
-    __shared__ int sval[WPB][256];
-    __shared__ __align__(8) u8 spos[WPB][256];     // list position of every byte value
+    __shared__ int sval[EWPB][256];
+    __shared__ __align__(8) u8 spos[EWPB][256];     // list position of every byte value
     __shared__ u32 sfreq[256];
     __shared__ u8 sused[256];
     __shared__ int s_nused;
-    __shared__ u32 s_front[WPB];
-    sfreq[threadIdx.x] = 0;
+    __shared__ u32 s_front[EWPB];
+    for (int k = threadIdx.x; k < 256; k += 32 * EWPB) sfreq[k] = 0;
     {   // compact list of the block's used byte values (ascending)
         const u32 *ub = usedbits + b * 8;
-        u32 t = threadIdx.x;
-        u32 before = 0;
-        for (u32 k = 0; k < (t >> 5); k++) before += __popc(ub[k]);
-        before += __popc(ub[t >> 5] & ((1u << (t & 31)) - 1));
-        if ((ub[t >> 5] >> (t & 31)) & 1) sused[before] = (u8)t;
-        if (t == 255) s_nused = (int)(before + ((ub[7] >> 31) & 1));
+        for (u32 t = threadIdx.x; t < 256; t += 32 * EWPB) {
+            u32 before = 0;
+            for (u32 k = 0; k < (t >> 5); k++) before += __popc(ub[k]);
+            before += __popc(ub[t >> 5] & ((1u << (t & 31)) - 1));
+            if ((ub[t >> 5] >> (t & 31)) & 1) sused[before] = (u8)t;
+            if (t == 255) s_nused = (int)(before + ((ub[7] >> 31) & 1));
+        }
     }
     __syncthreads();
     const int nused = s_nused;
@@ -206,5 +215,5 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_emit3(const u8 *Lall, const 
         }
     }
     __syncthreads();
-    if (sfreq[threadIdx.x]) atomicAdd(&freq[b * 256 + threadIdx.x], sfreq[threadIdx.x]);
+    for (int k = threadIdx.x; k < 256; k += 32 * EWPB) if (sfreq[k]) atomicAdd(&freq[b * 256 + k], sfreq[k]);
 }
