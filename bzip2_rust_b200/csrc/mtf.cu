@@ -86,20 +86,33 @@ __global__ void __launch_bounds__(BZ_THREADS) k_mtf_summary(const u8 *Lall, cons
     int first_nz = -1;      // position of the first non-zero rank in the chunk
     int last_nz = -1;       // running: last non-zero position seen so far (in chunk)
     u32 nnz = 0, digits = 0;
+    // the bytes of a step are loaded two steps ahead (a load used in the step that issues it costs its full latency on
+    // every one of the chunk's 64 steps); neighbours come from the lanes next door, the previous step's last byte and
+    // the next step's first one -- 0x200 stands for "no byte" (before the block / after its end: never equal)
+    auto ld = [&](u32 pos) { return pos < n ? (u32)L[pos] : 0x200u; };
+    u32 c0 = ld(a + lane), c1 = ld(a + 32 + lane);
+    u32 prev_last = a > 0 ? (u32)L[a - 1] : 0x200u;
     for (u32 i0 = a; i0 < e; i0 += 32) {
         u32 i = i0 + lane;
         bool in = i < e;
         bool nz = false, run_end = false;
-        const u32 chm = in ? (u32)L[i] : (0x100u | (u32)lane);
+        const u32 raw = c0;
+        c0 = c1; c1 = ld(i0 + 64 + lane);
+        const u32 chm = in ? raw : (0x100u | (u32)lane);
         {   // last occurrence of every byte value: positions grow with the lane, so the highest lane of each value wins
             const u32 peers = __match_any_sync(0xffffffffu, chm);
             if (in && (peers >> lane) == 1u) slast[w][chm] = (int)i;
         }
-        if (in) {
-            u32 ch = chm;
-            nz = is_nz(L, i, min_used);
-            bool nz_next = (i + 1 >= n) ? true : (L[i + 1] != ch);
-            run_end = !nz && nz_next;
+        {
+            u32 prev = __shfl_up_sync(0xffffffffu, raw, 1), next = __shfl_down_sync(0xffffffffu, raw, 1);
+            const u32 nfirst = __shfl_sync(0xffffffffu, c0, 0);
+            if (lane == 0) prev = prev_last;
+            if (lane == 31) next = nfirst;
+            prev_last = __shfl_sync(0xffffffffu, raw, 31);
+            if (in) {
+                nz = i == 0 ? (raw != min_used) : (raw != prev);
+                run_end = !nz && next != raw;
+            }
         }
         unsigned mnz = __ballot_sync(0xffffffffu, nz);
         if (first_nz < 0 && mnz) first_nz = (int)(i0 + __ffs(mnz) - 1);
