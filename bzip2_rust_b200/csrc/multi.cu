@@ -359,13 +359,13 @@ int bz2b200_compress_stream_multi(bz2b200_mctx *m, const uint8_t *in, size_t n, 
     m->in = in; m->nbytes = n; m->level = level; m->out = out; m->out_cap = out_cap;
     m->abort.store(0);
     {   // windows: a multiple of n_devices, at most 256 MiB each, whole 4 KiB pages
-        // Two windows per rank when four or more GPUs upload at once and a window still holds 32 MiB: the uploads then share
-        // the host's memory bandwidth (measured: 100 MB per GPU take 2.0 ms on 2 GPUs, 4.4 ms on 8) and the second window's
-        // upload hides under the first one's compression; a window costs about 1 ms of fixed work, which is more than
-        // the hidden copy on 1-2 GPUs (measured on 2 GPUs: 16.3 ms with one window per rank, 17.0 with two, 18.3 with three).
+        // Two windows per rank when a window still holds 32 MiB: nothing can be compressed before a rank's first window is on
+        // its device and the chain has passed the windows before it, and the second window's upload hides under the first
+        // one's kernels; a window costs about 0.8 ms of fixed work (measured, 2 GPUs x 100 MB: 17.2 ms with one window per
+        // rank, 15.8 ms with a quarter + three quarters; 8 GPUs: see profiles/r02_experiments.md section 6).
         const size_t WMAX = 256u << 20, WMIN = 32u << 20;
         size_t per_rank = (n + (size_t)m->n - 1) / (size_t)m->n;
-        size_t per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (per_rank >= 2 * WMIN && m->n >= 4) ? 2 : 1);
+        size_t per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (per_rank >= 2 * WMIN && m->n >= 2) ? 2 : 1);
         if (const char *e = getenv("BZ2B200_MULTI_WINDOWS")) { int v = atoi(e); if (v >= 1) per = std::max<size_t>((per_rank + WMAX - 1) / WMAX, (size_t)v); }
         // The first window of every rank is the smaller one (25% of its share): all ranks upload at once and share the
         // host's memory bandwidth, and nothing can be compressed before the first windows are on the devices (measured on
