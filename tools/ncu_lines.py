@@ -19,8 +19,9 @@ for r in csv.reader(io.StringIO(raw)):
         hdr = r
     elif r[0].isdigit() and hdr:
         d = dict(zip(hdr, r))
-        st = {k[6:]: int(v or 0) for k, v in d.items() if k.startswith("stall_") and "Not" not in k}
-        agg.append((cur, int(r[0]), r[1].strip()[:88], int(r[6] or 0), int(r[7] or 0), st))
+        num = lambda v: int(v) if v and v.strip("-").isdigit() else 0          # ncu prints "-" for lines without samples
+        st = {k[6:]: num(v) for k, v in d.items() if k.startswith("stall_") and "Not" not in k}
+        agg.append((cur, int(r[0]), r[1].strip()[:88], num(r[6]), num(r[7]), st))
 ts = sum(a[3] for a in agg) or 1
 ti = sum(a[4] for a in agg) or 1
 print("samples", ts, "warp instructions", ti)
