@@ -452,6 +452,9 @@ extern "C" int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, si
         for (size_t k = ci; k < ncand && starts.size() < NB; k++) {
             if (cand[k] & FOOT) continue;
             u64 re = k + 1 < ncand ? (cand[k + 1] & ~FOOT) : (u64)n * 8;
+            // no valid block is longer than 20 bits per symbol plus its header (symbol map, selectors, six tables): a
+            // damaged stream whose next magic is far away must not size the jump tables
+            re = std::min<u64>(re, cand[k] + (u64)20 * (max_block + 64) + ((u64)1 << 19));
             if (range_limit) re = std::min(re, cand[k] + range_limit);     // test knob: as if a chance magic cut the range
             starts.push_back(cand[k]); rends.push_back(re);
             max_range = std::max(max_range, re - cand[k]);
