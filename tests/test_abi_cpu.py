@@ -78,3 +78,27 @@ def test_bad_arguments_are_errors_not_crashes(lib):
     out = np.zeros(8, dtype=np.uint8)
     ln = C.c_size_t()
     assert lib.bz2b200_merge_streams(9, 0, None, None, None, None, out.ctypes.data, 8, C.byref(ln)) == bz.E_CAP
+
+
+def test_header_is_plain_c_and_every_symbol_links(lib, tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms), and a C caller that references every
+    declared entry point must link against the shared library (nothing is called except bz2b200_version)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    syms = _declared_symbols()
+    # bz2b200_sink is a callback TYPE, not a function of the library
+    syms = [s for s in syms if s != "bz2b200_sink"]
+    src = tmp_path / "abi.c"
+    src.write_text('#include "bz2b200.h"\n#include <stdio.h>\nint main(void) {\n    void *p[] = {%s};\n'
+                   '    printf("%%s %%d\\n", bz2b200_version(), (int)(sizeof p / sizeof p[0]));\n    return 0;\n}\n'
+                   % ", ".join("(void *)%s" % s for s in syms))
+    exe = tmp_path / "abi"
+    so = os.path.join(ROOT, "bzip2_rust_b200", "libbz2b200.so")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        so, "-Wl,-rpath," + os.path.dirname(so)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out and out.split()[-1] == str(len(syms))
