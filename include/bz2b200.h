@@ -139,12 +139,14 @@ int bz2b200_zstream_close(bz2b200_zstream *z, uint64_t *total_in, uint64_t *tota
 /* The reference fans blocks out to rayon workers (compress.rs:125-132) and a writer thread puts them back in
  * order (compress.rs:74-122).  A multi context owns n_devices single-GPU contexts and one host thread per GPU
  * (device_ids == NULL: devices 0 .. n_devices-1; an id may repeat).  bz2b200_compress_stream_multi cuts the input
- * into n_devices contiguous slices; every GPU uploads and scans its slice, the block chain (rle1.rs:245-264) is
- * handed from GPU to GPU as one number through host memory, every GPU compresses the blocks that start in its
- * slice and copies its bit string, pre-shifted to its final bit phase, over its own PCIe link straight into
- * `out`; the calling thread ORs the seam bytes, folds the combined CRC (crc.rs:25-27) and writes header and
- * footer (bitwriter.rs:67-72, :103-114).  No collective, no NCCL.  `out` holds exactly the bytes
- * bz2b200_compress_stream produces for the same input, for every n_devices.  Pass page-locked `in` / `out`
+ * into windows dealt round robin to the GPUs (two per GPU, the first one a quarter of its share; at most 256 MiB
+ * each); a GPU uploads and scans a window while it compresses the one before, the uploads of all GPUs are ordered like
+ * the windows, the block chain (rle1.rs:245-264) is handed from window to window as one number through host memory,
+ * every GPU compresses the blocks that start in its windows and copies each bit string, pre-shifted to its final bit
+ * phase, over its own PCIe link straight into `out`; the calling thread ORs the seam bytes, folds the combined CRC
+ * (crc.rs:25-27) and writes header and footer (bitwriter.rs:67-72, :103-114).  No collective, no NCCL.  `out` holds
+ * exactly the bytes bz2b200_compress_stream produces for the same input, for every n_devices.  Pass page-locked
+ * `in` / `out`
  * for full copy overlap.  One call at a time per multi context. */
 typedef struct bz2b200_mctx bz2b200_mctx;
 int  bz2b200_create_multi(int n_devices, const int *device_ids, bz2b200_mctx **out);

@@ -102,3 +102,12 @@ def test_header_is_plain_c_and_every_symbol_links(lib, tmp_path):
     assert r.returncode == 0, r.stdout
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout
     assert "sm_100a" in out and out.split()[-1] == str(len(syms))
+
+
+def test_rust_binding_declares_the_header(lib):
+    """integration/rust/bz2b200-sys/src/lib.rs (unbuilt here: no rustc) must declare exactly the functions of the header."""
+    text = open(os.path.join(ROOT, "integration", "rust", "bz2b200-sys", "src", "lib.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (bz2b200_[a-z0-9_]+)\s*\(", text)))
+    declared = [s for s in _declared_symbols() if s != "bz2b200_sink"]
+    assert rust == declared
+    assert "pub type bz2b200_sink" in text
