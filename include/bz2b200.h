@@ -185,7 +185,8 @@ int bz2b200_huffman(bz2b200_ctx *ctx, const uint16_t *sym, uint32_t m, const uin
                     uint8_t *lengths, uint8_t *selectors, int *table_count);
 /* bwt_decode (src/bwt_algorithms/bwt_sort.rs:91) */
 int bz2b200_bwt_decode(bz2b200_ctx *ctx, uint32_t key, const uint8_t *bwt, uint32_t n, uint8_t *out);
-/* decompress (src/compression/decompress.rs:38): single bzip2 stream, CRCs enforced */
+/* decompress (src/compression/decompress.rs:38): what libbz2 accepts -- one or several bzip2 streams one after the
+ * other, legacy randomised blocks; block and combined CRCs are enforced (the reference only logs a mismatch) */
 int bz2b200_decompress_stream(bz2b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
                               size_t *out_len);
 
