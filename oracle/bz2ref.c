@@ -1123,3 +1123,32 @@ int ref_decompress_stream_reference(const uint8_t *in, size_t n, uint8_t *out, s
     if (n_crc_mismatch) *n_crc_mismatch = 0;
     return decompress_impl(in, n, out, cap, out_len, 1, n_blocks, n_crc_mismatch);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Test hooks for the reference's own bit-stream unit vectors                  */
+/* (bitwriter.rs:179-210, bitreader.rs:175-240): the stream writer and the    */
+/* decoder's bit reader above, driven call by call.                           */
+/* ------------------------------------------------------------------------- */
+/* BitWriter::out8 for every byte of `bytes`, then flush (bitwriter.rs:135-172); returns the output length */
+size_t ref_bw_out8_flush(const uint8_t *bytes, size_t n, uint8_t *out, size_t cap) {
+    bitwriter w = { out, 0, cap, 0, 0, 0 };
+    for (size_t i = 0; i < n; i++) bw_out8(&w, bytes[i]);
+    bw_flush(&w);
+    return w.overflow ? (size_t)-1 : w.len;
+}
+/* BitReader::bint(k) / bit / byte (bitreader.rs:60-150) as a sequence of reads: widths[i] bits each, MSB first;
+ * values[i] receives the value, *bitpos_out the position after the last read ("[byte.bit]" of BitReader::loc);
+ * returns the number of reads that were served before the input ran out */
+size_t ref_br_read_sequence(const uint8_t *in, size_t n, const int *widths, size_t nreads, uint32_t *values,
+                            size_t *bitpos_out) {
+    bitrd r = { in, n, 0, 0 };
+    size_t done = 0;
+    for (size_t i = 0; i < nreads; i++) {
+        uint32_t v = rd_bits(&r, widths[i]);
+        if (r.eof) break;
+        values[i] = v; done++;
+    }
+    if (bitpos_out) *bitpos_out = r.bitpos;
+    return done;
+}
+

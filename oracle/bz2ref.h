@@ -106,6 +106,10 @@ void ref_bp_out24(ref_bitpacker *bp, uint32_t data);
 void ref_bp_out32(ref_bitpacker *bp, uint32_t data);
 void ref_bp_out16(ref_bitpacker *bp, uint16_t data);
 void ref_bp_flush(ref_bitpacker *bp);
+/* test hooks for the reference's bitwriter / bitreader unit vectors (bitwriter.rs:179-210, bitreader.rs:175-240) */
+size_t ref_bw_out8_flush(const uint8_t *bytes, size_t n, uint8_t *out, size_t cap);
+size_t ref_br_read_sequence(const uint8_t *in, size_t n, const int *widths, size_t nreads, uint32_t *values,
+                            size_t *bitpos_out);
 
 int ref_huf_encode(ref_bitpacker *bp, const uint16_t *rle2, uint32_t m, const uint32_t freq[256],
                    uint16_t eob, const uint16_t *symmap, int nmap, ref_huf_info *info);

@@ -311,3 +311,29 @@ class Packer:
     def loc(self):
         b = self._bp.len * 8 + self._bp.q_bits
         return "[%d.%d]" % (b // 8, b % 8)
+
+
+def bw_out8_flush(data):
+    """BitWriter::out8 for every byte, then flush (bitwriter.rs:135-172): the reference's bitwriter unit vectors."""
+    data = bytes(data)
+    buf = C.create_string_buffer(len(data) + 8)
+    L = lib()
+    L.ref_bw_out8_flush.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.ref_bw_out8_flush.restype = C.c_size_t
+    n = L.ref_bw_out8_flush(data, len(data), buf, len(data) + 8)
+    return buf.raw[:n]
+
+
+def br_read(data, widths):
+    """The decoder's bit reader driven like BitReader::bit / bint / byte (bitreader.rs:52-150): one read per width,
+    MSB first -> (values served before the input ran out, "[byte.bit]" position as BitReader::loc prints it)."""
+    data = bytes(data)
+    w = (C.c_int * len(widths))(*widths)
+    v = (C.c_uint32 * len(widths))()
+    pos = C.c_size_t()
+    L = lib()
+    L.ref_br_read_sequence.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_size_t)]
+    L.ref_br_read_sequence.restype = C.c_size_t
+    done = L.ref_br_read_sequence(data, len(data), w, len(widths), v, C.byref(pos))
+    return [int(v[i]) for i in range(done)], "[%d.%d]" % (pos.value // 8, pos.value % 8)

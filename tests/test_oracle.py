@@ -194,3 +194,21 @@ def test_huffman_ties_stay_out_of_the_unpinned_window(ref):
                        ("mixed", corpus.mixed(2_000_000, 5))):
         _, st = ref.compress_stream(data.tobytes(), 9, ref.SPEC_FAST, threads=4, want_stats=True)
         assert st["tie_unpinned"] == 0, (name, st["tie_events"], st["tie_unpinned"])
+
+
+# ---- the reference's bit-stream unit vectors (bitwriter.rs:179-210, bitreader.rs:175-238) ----------------------
+def test_bitwriter_out8_vectors(ref):          # bitwriter.rs:179-210
+    assert ref.bw_out8_flush(b"x") == b"x"                                                  # out8_test
+    assert ref.bw_out8_flush(bytes([255, 1, 128, 255, 7 << 5])) == bytes([255, 1, 128, 255, 224])   # last_bits_test_1
+    assert ref.bw_out8_flush(bytes([255, 6 << 5])) == bytes([0b1111_1111, 0b1100_0000])     # out24_short_test
+
+
+def test_bitreader_vectors(ref):               # bitreader.rs:175-238
+    assert ref.br_read(bytes([0b10000001]), [1] * 9) == ([1, 0, 0, 0, 0, 0, 0, 1], "[1.0]")   # basic_test: the ninth read is None
+    assert ref.br_read(bytes([0b00011011]), [5, 1, 2])[0] == [3, 0, 3]                         # bint_test
+    hello = b"Hello, world!"
+    assert ref.br_read(hello, [8] * 4)[0] == list(b"Hell")                                    # byte_test
+    assert bytes(ref.br_read(hello, [8] * 5)[0]) == b"Hello"                                  # bytes_test
+    assert ref.br_read(hello, [8] * 5 + [1])[1] == "[5.1]"                                    # loc_test
+    assert [bool(b) for b in ref.br_read(bytes([0b01010000]), [1] * 8)[0]] == \
+        [False, True, False, True, False, False, False, False]                                # bool_bit_test
